@@ -1,0 +1,123 @@
+"""Pin the oracle: every restatement in oracle/ vs fixtures produced by the
+unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import repellency_oracle as orc
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def fast_fx():
+    return np.load(os.path.join(G, "fast_cases.npz"))
+
+
+@pytest.mark.parametrize("tag,sdv3", [("fast", False), ("sdv3", True)])
+@pytest.mark.parametrize("q", [1, 3])
+@pytest.mark.parametrize("regime", ["far", "x0", "near", "mid"])
+def test_fast_closed_form_matches_reference(fast_fx, tag, sdv3, q, regime):
+    bank = fast_fx[f"{tag}/bank"]
+    key = f"{tag}/q{q}/{regime}"
+    x = fast_fx[key + "/x"]
+    r = orc.conditioning_fast(x, bank, scale=0.03, sigma=1.0, sdv3=sdv3)
+    # reference is fp32: agree to fp32 rounding of the expansion (2-5e-7 typical)
+    assert rel(r["neg"], fast_fx[key + "/neg"]) < 5e-5
+    assert rel(r["x_0_hat"], fast_fx[key + "/x0"]) < 1e-6
+    assert abs(r["mean_x_0_hat"] - float(fast_fx[key + "/item"])) < 1e-6 * max(1.0, abs(r["mean_x_0_hat"]))
+
+
+@pytest.mark.parametrize("q", [1, 3])
+@pytest.mark.parametrize("regime", ["far", "x0", "near", "mid"])
+def test_materialised_port_matches_reference(fast_fx, q, regime):
+    for tag, sdv3 in (("fast", False), ("sdv3", True)):
+        bank = torch.from_numpy(fast_fx[f"{tag}/bank"])
+        key = f"{tag}/q{q}/{regime}"
+        x = torch.from_numpy(fast_fx[key + "/x"]).clone()
+        neg, item, _, _ = orc.materialised_port(x.clone(), bank, 1.0, 1e-8, normalise_query=sdv3)
+        np.testing.assert_allclose(neg.numpy(), fast_fx[key + "/neg"], rtol=1e-5, atol=1e-7)
+        x0, _, _ = orc.conditioning_port(x, bank, 0.03, normalise_query=sdv3)
+        np.testing.assert_allclose(x0.numpy(), fast_fx[key + "/x0"], rtol=1e-6, atol=1e-7)
+
+
+def test_threshold_cases_match_reference():
+    fx = np.load(os.path.join(G, "threshold_cases.npz"))
+    bank = fx["thr/bank"]
+    seen_gate = set()
+    for sigma in (3.15, 1.0, 13.15):
+        for regime in ("far", "x0", "near", "mid"):
+            key = f"thr/s{sigma}/{regime}"
+            sg, scale, thr, margin = fx[key + "/params"]
+            x = fx[key + "/x"]
+            r = orc.conditioning_threshold(x, bank, sg, scale, 1e-8, thr, margin, use_gate=True)
+            assert rel(r["x_0_hat"], fx[key + "/gate/x0"]) < 1e-5
+            assert rel(r["denominator"], fx[key + "/gate/denominator"]) < 2e-5
+            assert rel(r["nominator"], fx[key + "/gate/nominator"]) < 5e-5
+            assert bool(r["is_negation"][0]) == bool(fx[key + "/gate/is_negation"])
+            seen_gate.add(bool(r["is_negation"][0]))
+            r = orc.conditioning_threshold(x, bank, sg, scale, 1e-8, thr, margin, use_gate=False)
+            assert rel(r["x_0_hat"], fx[key + "/nogate/x0"]) < 5e-5          # negative mean (Q5)
+            assert rel(r["x_0_hat_inplace"], fx[key + "/nogate/x_inplace"]) < 1e-5
+            assert bool(fx[key + "/nogate/is_negation"]) is True
+    assert seen_gate == {True, False}, "fixtures must exercise both gate outcomes"
+
+
+def test_empirical_beta_matches_reference():
+    fx = np.load(os.path.join(G, "beta_cases.npz"))
+    bank = fx["beta/bank"]
+    ts = [int(t) for t in fx["beta/timesteps"]]
+    noisy = {t: fx[f"beta/noisy/{t}"] for t in ts}
+    for qt in (0.0, 0.25):
+        got = orc.empirical_beta(noisy, bank, sigma=3.15, quantile=qt)
+        np.testing.assert_allclose([got[t] for t in ts], fx[f"beta/q{qt}"], rtol=2e-5)
+
+
+def test_sparse_matches_reference():
+    fx = np.load(os.path.join(G, "sparse_cases.npz"))
+    bank = fx["sparse/bank"]
+    outcomes = set()
+    for tag in ("fast", "thr"):
+        for radius in (4.0, 11.5, 13.0):
+            for regime in ("near", "x0", "mid"):
+                key = f"sparse/{tag}/r{radius}/{regime}"
+                r = orc.sparse_repellency(fx[key + "/x"], bank, radius, scale=1.6)
+                assert rel(r["x_0_hat"], fx[key + "/x0"]) < 2e-5, key
+                assert abs(r["force_norm"] - float(fx[key + "/item"])) <= 2e-4 * max(1.0, r["force_norm"])
+                if tag == "thr":
+                    assert r["is_negation"] == bool(fx[key + "/is_negation"])
+                    outcomes.add(r["is_negation"])
+    assert outcomes == {True, False}
+
+
+def test_known_answers_sd14_shape():
+    """SURVEY 8c anchors at 515x4x64x64, regenerated from seeds."""
+    ka = json.load(open(os.path.join(G, "known_answers.json")))
+    g = torch.Generator().manual_seed(1234)
+    bank = torch.randn(515, 4, 64, 64, generator=g)
+    bank /= bank.norm(dim=1, keepdim=True)
+    g2 = torch.Generator().manual_seed(4321)
+    xf = torch.randn(1, 4, 64, 64, generator=g2)
+    xn = bank[7:8] + 0.05 * torch.randn(1, 4, 64, 64, generator=g2)
+    b = bank.numpy()
+    for name, x in (("xf", xf), ("half_xf", 0.5 * xf), ("xn", xn)):
+        r = orc.conditioning_threshold(x.numpy(), b, 3.15, 0.33, 1e-8, 1e-9, 0.0, True)
+        want = ka[f"threshold/{name}"]
+        assert abs(r["denominator"][0] / want["denominator"] - 1) < 2e-5
+        assert abs(r["x_0_hat"].sum() - want["sum_x0"]) < 1e-3
+        np.testing.assert_allclose(r["x_0_hat"].reshape(-1)[:8], want["x0_first8"], rtol=1e-5)
+        assert abs(np.abs(r["x_0_hat"] - x.numpy()).max() - want["max_abs_delta"]) < 1e-6
+    for name, x in (("xf", xf), ("xn", xn)):
+        r = orc.conditioning_fast(x.numpy(), b, scale=0.03, sigma=1.0)
+        want = ka[f"fast/{name}"]
+        assert abs(np.abs(r["x_0_hat"] - x.numpy()).max() - want["max_abs_delta"]) < 1e-6
+        assert abs(r["mean_x_0_hat"] - want["mean_x_0_hat"]) < 2e-3 * abs(want["mean_x_0_hat"]) + 1e-30
