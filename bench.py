@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- repellency projections / second on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one conditioning() call over one batch of Q synthetic queries: query prepare ->
+partial sums over the (N-sharded) negative bank -> [one NCCL all-reduce when N > 1] -> fused
+correction epilogue.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (Q, N, C, H, W, module semantics, sigma, scale) -- BASELINE.json configs
+    "cfg1": dict(Q=1, N=515, C=4, H=64, W=64, kind="fast", sigma=1.0, scale=0.03),
+    "cfg2": dict(Q=16, N=515, C=4, H=64, W=64, kind="threshold", sigma=3.15, scale=0.33),
+    "cfg3": dict(Q=64, N=3000, C=4, H=64, W=64, kind="fast", sigma=1.0, scale=0.03),
+    "cfg4": dict(Q=16, N=515, C=16, H=128, W=128, kind="fast_sdv3", sigma=1.0, scale=0.03),
+    "cfg5": dict(Q=128, N=30000, C=4, H=64, W=64, kind="threshold", sigma=3.15, scale=0.33),
+}
+WORKLOAD_TEXT = {
+    "cfg1": "SD-1.4 latent projection, B=1, N=515, 4x64x64 fp32 (BASELINE configs[0])",
+    "cfg2": "SD-1.4 nudity, B=8 with CFG (Q=16 rows), N=515, 4x64x64 (BASELINE configs[1], projection only)",
+    "cfg3": "CoPro inappropriate bank: N=3000 negatives, B=32 with CFG (Q=64 rows), 4x64x64 fp32, N-sharded "
+            "(BASELINE configs[2]; north_star target shape)",
+    "cfg4": "SD3 path: 16x128x128 latents, N=515, Q=16, query channel-normalised (BASELINE configs[3])",
+    "cfg5": "threshold variant, scaled bank N=30000, Q=128, 4x64x64 (BASELINE configs[4])",
+}
+FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 stream, 3 umma")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_arm(wl, steps, warmup, sample_q=4):
+    """The reference's CPU path: oracle.materialised_port (same op chain as fast.py:249-257) on all
+    host threads.  One step = conditioning of `sample_q` query rows against the full bank."""
+    import torch
+    from oracle import repellency_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bank = orc.synthetic_bank(wl["N"], wl["C"], wl["H"], wl["W"])
+    q = min(sample_q, wl["Q"])
+    x = orc.synthetic_queries(bank, q, "near")
+    sdv3 = wl["kind"] == "fast_sdv3"
+    sigma = wl["sigma"]
+    for _ in range(max(warmup, 1)):
+        orc.conditioning_port(x.clone(), bank, wl["scale"], sigma, 1e-8, sdv3)
+    times = []
+    for _ in range(steps):
+        xin = x.clone()
+        t0 = time.perf_counter()
+        orc.conditioning_port(xin, bank, wl["scale"], sigma, 1e-8, sdv3)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": q * steps / total, "unit": "projections/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"{steps} calls x {q} query rows (of Q={wl['Q']}) against the full N={wl['N']} bank, "
+                      f"float32 torch op chain of the reference (oracle.materialised_port); "
+                      f"best call {min(times)*1e3:.1f} ms",
+            "ms_per_step": 1e3 * total / steps, "q": q}
+
+
+# ----------------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    Q, N, C, H, W = wl["Q"], wl["N"], wl["C"], wl["H"], wl["W"]
+    D = C * H * W
+    base = {"metric": "repellency projections/sec", "unit": "projections/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[args.workload], "Q": Q, "N": N, "latent": [C, H, W],
+                       "sigma": wl["sigma"], "scale": wl["scale"], "semantics": wl["kind"],
+                       "parallelism": f"N-sharded bank over {args.gpus} GPU(s), one NCCL all-reduce of [Q,D+1] fp32"
+                       if args.gpus > 1 else "single GPU"}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 10))
+        r = cpu_reference_arm(wl, steps, min(args.warmup, 1))
+        line = dict(base)
+        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
+                     "steps": steps, "warmup": min(args.warmup, 1), "n_gpus": args.gpus,
+                     "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                     "e2e": {"value": r["value"], "unit": "projections/s", "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        line["config"] = dict(base["config"], note="reference arm: the reference is pure Python with no "
+                              "package to install; its CPU op chain is timed via the oracle port on the host cores")
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from safe_denoiser_b200 import _native as nv
+    from safe_denoiser_b200.projection import NegativeBank, Projector, conditioning_host, shard_bounds
+    from oracle import repellency_oracle as orc   # synthetic inputs + cpu_baseline only
+
+    nv.lib()   # raises if the CUDA library is missing: no fallback
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    bank_cpu = orc.synthetic_bank(N, C, H, W)
+    lo, hi = shard_bounds(N, rank, world)
+    bank = NegativeBank(bank_cpu[lo:hi].to(dev), with_planes=(args.path in (0, 3)))
+    proj = Projector(bank, path=args.path, group=group)
+    x_src = orc.synthetic_queries(bank_cpu, Q, "near").to(dev)
+    x = x_src.clone()
+    normalize = C if wl["kind"] == "fast_sdv3" else 0
+    sigma, scale, eps = wl["sigma"], wl["scale"], 1e-8
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step():
+        proj.correct(x, sigma, scale, eps, normalize_channels=normalize,
+                     gate_threshold=(1.0 if wl["kind"] == "threshold" else None))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        x.copy_(x_src)
+        step()
+    barrier()
+
+    # ---- timed region: K steps, each between its own CUDA events, L2 flushed in between ----
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = nv.launch_count()
+    barrier()
+    for i in range(args.steps):
+        x.copy_(x_src)
+        flush.zero_()
+        ev0[i].record()
+        step()
+        ev1[i].record()
+    barrier()
+    launches = nv.launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = Q * args.steps / (total_ms * 1e-3)
+
+    # ---- the bank-streaming stage alone (roofline): events around sdn_repel_partial ----
+    s = proj._get(Q, normalize > 0)
+    p0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    p1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    group_saved, proj.group = proj.group, None          # the kernel(s) only, no collective
+    x.copy_(x_src)
+    for i in range(args.steps):
+        flush.zero_()
+        # query prepare is part of partial_sums(); time only the projection kernels by event placement
+        L, st = nv.lib(), nv.current_stream()
+        xf = x.view(Q, D)
+        nv.check(L.sdn_query_prepare(nv.ptr(xf), None, 1.0, 0.0, Q, D, normalize, None,
+                                     nv.ptr(s.xq) if normalize else None, nv.ptr(s.xsq), st))
+        query = s.xq if normalize else xf
+        p0[i].record()
+        nv.check(L.sdn_repel_partial(nv.ptr(bank.flat), nv.ptr(bank.sqnorm), nv.ptr(bank.planes), bank.N, D,
+                                     nv.ptr(query), nv.ptr(s.xsq), Q, 1.0 / (2 * sigma * sigma), 1, 1.0,
+                                     nv.ptr(s.num), nv.ptr(s.z), None, nv.ptr(s.ws), s.ws_bytes, args.path, st))
+        p1[i].record()
+    torch.cuda.synchronize()
+    proj.group = group_saved
+    part_ms = sorted(a.elapsed_time(b) for a, b in zip(p0, p1))
+    part_avg_ms = sum(part_ms) / len(part_ms)
+    sampler.stop()
+
+    # ---- e2e: host buffers through the public call, copies inside the timed region ----
+    xh_src = x_src.cpu().contiguous()
+    xh = xh_src.clone().pin_memory()
+    dh = torch.empty(Q, dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 50))
+
+    def e2e_step():
+        if world == 1:
+            conditioning_host(bank, xh, dh, sigma, scale, eps, normalize_channels=normalize, path=args.path)
+        else:
+            x.copy_(xh, non_blocking=True)
+            proj.correct(x, sigma, scale, eps, normalize_channels=normalize)
+            xh.copy_(x, non_blocking=True)
+            dh.copy_(proj._get(Q, False).denom, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(3):
+        xh.copy_(xh_src)
+        e2e_step()
+    barrier()
+    e2e_total = 0.0
+    for _ in range(e2e_steps):
+        xh.copy_(xh_src)
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_total += time.perf_counter() - t0
+    te = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = Q * e2e_steps / float(te.item())
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        n_local = hi - lo
+        algo_bytes = n_local * D * 4 + n_local * 4 + 2 * Q * D * 4
+        achieved = algo_bytes / (part_avg_ms * 1e-3) / 1e9
+        line = dict(base)
+        line["config"] = dict(base["config"],
+                              l2="flushed between steps (256 MiB memset outside the per-step events)",
+                              timing="sum of per-step CUDA-event intervals, max over ranks",
+                              kernel_path=args.path,
+                              e2e_call="sdn_conditioning_host (C ABI, pinned host buffers)" if world == 1
+                              else "pinned host -> Projector.correct (N-sharded) -> pinned host")
+        line.update({
+            "value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "projections/s", "h2d_bytes_per_step": Q * D * 4,
+                    "d2h_bytes_per_step": Q * D * 4 + Q * 4, "steps": e2e_steps},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "sdn_repel_partial (bank-streaming projection stage, per-GPU shard)",
+                         "algorithmic_bytes": algo_bytes, "avg_ms": part_avg_ms, "min_ms": part_ms[0],
+                         "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
+            "clocks": sampler.summary(),
+        })
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_reference_arm(wl, steps=5, warmup=1)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/*
+ * sdn_repel.h -- C ABI of the B200-native repellency projection.
+ *
+ * The reference (MingyuKim87/Safe_Denoiser) is pure Python and has no FFI; the
+ * boundary it exposes for this path is the Python object returned by
+ * get_repellency_method() (repellency/repellency_methods_fast.py:19-22) and its
+ * .conditioning(x_0_hat) method (:120-132).  Every entry point below replaces
+ * one slice of what that method does with torch ops; the reference lines are
+ * cited per function.  The modules under safe_denoiser_b200/repellency/ are the host-side
+ * mirror of the reference interface and bind these symbols through ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch types, nothing thrown;
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - no hidden allocation: scratch is caller-provided, its size comes from
+ *     the matching *_workspace_bytes() call (the *_host convenience calls are
+ *     the exception: they own a cached pinned/device staging area);
+ *   - return value: 0 ok; <0 invalid argument (SDN_E_*); >0 a cudaError_t.
+ *   - all tensors are contiguous row-major fp32 unless stated.
+ *
+ * Shapes: Q query rows, N negatives in (this shard of) the bank, D = C*H*W.
+ */
+#ifndef SDN_REPEL_H_
+#define SDN_REPEL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDN_ABI_VERSION 1
+
+enum {
+  SDN_OK = 0,
+  SDN_E_NULL = -1,        /* required pointer is NULL */
+  SDN_E_SHAPE = -2,       /* non-positive or inconsistent size */
+  SDN_E_ALIGN = -3,       /* pointer / D not aligned as required (16 B, D % 4 == 0) */
+  SDN_E_PARAM = -4,       /* unsupported dist_power / mode / flag */
+  SDN_E_WORKSPACE = -5,   /* workspace too small */
+  SDN_E_UNSUPPORTED = -6, /* shape outside what the selected kernel family handles */
+  SDN_E_DEVICE = -7       /* not an sm_100 device */
+};
+
+/* Kernel family selector for sdn_repel_partial (SDN_PATH_AUTO picks by shape). */
+enum {
+  SDN_PATH_AUTO = 0,
+  SDN_PATH_GENERIC = 1,   /* CUDA-core two-phase kernels, any shape */
+  SDN_PATH_STREAM = 2,    /* one-pass cluster kernel, GEMV-shaped (small Q) */
+  SDN_PATH_UMMA = 3       /* tcgen05 / TMEM / TMA two-phase kernels, batched Q */
+};
+
+/* Epilogue flags (bit-or). */
+enum {
+  SDN_EPI_GATE = 1,          /* apply the beta gate: row q is re-noised only if Z_q + eps > gate_threshold
+                                (threshold.py:181-185); without it every row is treated as negated */
+  SDN_EPI_RETURN_NEG = 2     /* the tensor handed on to the re-noise is the negative mean, not the
+                                corrected x0 (threshold.py:190-193) */
+};
+
+int sdn_abi_version(void);
+const char* sdn_error_string(int code);
+/* Number of kernels this library has launched since load (all entry points); bench.py reports it. */
+uint64_t sdn_launch_count(void);
+
+/* ---- bank -------------------------------------------------------------------------------
+ * Derived data of the proj_ref tensor, computed once at load (fast.py:109-111 loads the tensor;
+ * torch.cdist recomputes ||n_i||^2 on every call, fast.py:249).
+ *   sqnorm_out [N]        fp32 ||n_i||^2
+ *   planes_out [2][N][D]  bf16 hi plane then lo plane (hi = bf16(n), lo = bf16(n - hi)); may be NULL
+ */
+int sdn_bank_prepare(const float* bank, int64_t N, int64_t D,
+                     float* sqnorm_out, void* planes_out, void* stream);
+
+/* ---- query ------------------------------------------------------------------------------
+ * x0 = c_x * x_in + c_m * model_out   (model_out may be NULL -> x0 = c_x * x_in)
+ *   DDPM eps-prediction (diffusers DDPMScheduler.step -> pred_original_sample, called at
+ *   ...threshold_time.py:554): c_x = 1/sqrt(abar_t), c_m = -sqrt(1-abar_t)/sqrt(abar_t)
+ *   SD3 flow (safe_denoiser_pipeline.py:1146): c_x = 1, c_m = -sigma
+ * xq = x0, or x0 divided by its per-pixel L2 norm over the C channels when normalize_C > 0
+ *   (fast_sdv3.py:239; D = normalize_C * HW).
+ * x0_out [Q,D] (may alias x_in; may be NULL if not wanted), xq_out [Q,D] (may be NULL when
+ * normalize_C == 0 and x0_out is given: then xq == x0), xsq_out [Q] = ||xq||^2.
+ */
+int sdn_query_prepare(const float* x_in, const float* model_out, float c_x, float c_m,
+                      int64_t Q, int64_t D, int32_t normalize_C,
+                      float* x0_out, float* xq_out, float* xsq_out, void* stream);
+
+/* ---- projection -------------------------------------------------------------------------
+ * Un-normalised sums over the rows of this bank (shard):
+ *   dist_qi = sqrt(max(||xq||^2 + a^2 ||n_i||^2 - 2 a xq.n_i, 0))      (dist_power 1, the reference,
+ *             fast.py:249: torch.cdist, un-squared)   or the squared form (dist_power 2, fast.py:413)
+ *   k_qi    = exp(-dist_qi * inv_two_sigma_sq)                           (raw exp, no max-shift, Q3)
+ *   num_out [Q,D] = sum_i k_qi n_i ,  z_out [Q] = sum_i k_qi             (fast.py:250; the ones column)
+ * k_out [Q,N] receives k_qi when non-NULL (tests / weights parity).  num_out may be NULL when only
+ * z_out is wanted (empirical_beta, threshold.py:351-384).
+ * N-sharding: run this per shard, all-reduce(sum) num_out and z_out, then call an epilogue.
+ */
+size_t sdn_repel_workspace_bytes(int64_t Q, int64_t N, int64_t D, int32_t path);
+
+int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes,
+                      int64_t N, int64_t D,
+                      const float* xq, const float* xsq, int64_t Q,
+                      float inv_two_sigma_sq, int32_t dist_power, float bank_alpha,
+                      float* num_out, float* z_out, float* k_out,
+                      void* workspace, size_t workspace_bytes, int32_t path, void* stream);
+
+/* ---- epilogues (one pass over Q*D) ------------------------------------------------------
+ * Common part (fast.py:253-257, :131; threshold.py:181-187):
+ *   denom_q = z_q + eps ; neg = num / denom_q ; gate_q = !(flags&GATE) || denom_q > gate_threshold
+ *   x0c = x0 - scale * neg
+ * Outputs that may be NULL are skipped.  mean_out[0] += sum(clamp(neg, +-1e10)) / (Q*D)  (the
+ * reference's logging scalar, fast.py:258); the caller zeroes it.
+ */
+
+/* conditioning(): x0_inout <- x0c in place (Q8); neg_out [Q,D]; denom_out [Q]; gate_out [Q] int32.
+ * x0_inout may be NULL when only neg_out is wanted (empirical_denoiser alone, fast.py:223-262). */
+int sdn_epilogue_correct(const float* num, const float* z, int64_t Q, int64_t D,
+                         float eps, float scale, float gate_threshold, int32_t flags,
+                         float* x0_inout, float* neg_out, float* denom_out, int32_t* gate_out,
+                         float* mean_out, void* stream);
+
+/* SD-1.4 in-window step (...threshold_time.py:554-576 with diffusers DDPMScheduler):
+ *   x0 = (x_t - s1 eps)/sa ; src = RETURN_NEG ? neg : x0c
+ *   x_t' = gate ? sa*src + s1*z1 : x_t ; x0'' = (x_t' - s1 eps)/sa
+ *   latents_out = c_x0*x0'' + c_xt*x_t' + sigma_noise*z2
+ * with sa = sqrt(abar_t), s1 = sqrt(1-abar_t).  z2 may be NULL when sigma_noise == 0.
+ * x0c_out [Q,D] optional (the corrected x0 the reference would have returned).
+ */
+int sdn_epilogue_ddpm(const float* num, const float* z, int64_t Q, int64_t D,
+                      float eps, float scale, float gate_threshold, int32_t flags,
+                      const float* x_t, const float* eps_pred, const float* z1, const float* z2,
+                      float sqrt_ab, float sqrt_1m_ab, float c_x0, float c_xt, float sigma_noise,
+                      float* latents_out, float* x0c_out, float* denom_out, int32_t* gate_out,
+                      float* mean_out, void* stream);
+
+/* DDIM (eta = 0) variant: latents_out = sqrt_ab_prev * x0'' + sqrt_1m_ab_prev * eps. */
+int sdn_epilogue_ddim(const float* num, const float* z, int64_t Q, int64_t D,
+                      float eps, float scale, float gate_threshold, int32_t flags,
+                      const float* x_t, const float* eps_pred, const float* z1,
+                      float sqrt_ab, float sqrt_1m_ab, float sqrt_ab_prev, float sqrt_1m_ab_prev,
+                      float* latents_out, float* x0c_out, float* denom_out, int32_t* gate_out,
+                      float* mean_out, void* stream);
+
+/* SD3 flow-matching step (safe_denoiser_pipeline.py:1142-1161):
+ *   x0 = x - sigma v ; x1 = x + (1-sigma) v ; noise = sqrt(sigma_next) x1 + sqrt(1-sigma_next) zn
+ *   latents_out = x0c + sigma_next (noise - x0c)
+ */
+int sdn_epilogue_flow(const float* num, const float* z, int64_t Q, int64_t D,
+                      float eps, float scale,
+                      const float* x, const float* v, const float* zn,
+                      float sigma, float sigma_next,
+                      float* latents_out, float* x0c_out, float* denom_out,
+                      float* mean_out, void* stream);
+
+/* ---- SPELL baseline (fast.py:306-340, threshold.py:415-454) ------------------------------
+ * dist_out [Q,N] = ||x_q - n_i|| from the same expansion; the force is
+ *   term_q = sum_i relu(radius/d_qi - 1) (x_q - n_i) ; x0_inout += scale * term.
+ * wsum_out [Q] = sum_i relu(radius/d_qi - 1)  (is_negation = wsum != 0, threshold.py:447-450).
+ */
+int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t D,
+                     float* x0_inout, const float* xsq, int64_t Q,
+                     float radius, float scale,
+                     float* term_out, float* wsum_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- host-buffer convenience: the e2e path ------------------------------------------------
+ * One conditioning() call with HOST tensors: H2D of x0_host [Q,D], projection over a device-resident
+ * prepared bank, correction, D2H of the corrected x0 (in place) and denom_host [Q].  Synchronous.
+ * normalize_C as in sdn_query_prepare.  The staging buffers are cached inside the library and
+ * released by sdn_host_release().
+ */
+int sdn_conditioning_host(const float* bank, const float* sqnorm, const void* planes,
+                          int64_t N, int64_t D,
+                          float* x0_host, int64_t Q, int32_t normalize_C,
+                          float inv_two_sigma_sq, int32_t dist_power, float bank_alpha,
+                          float eps, float scale,
+                          float* denom_host, int32_t path, void* stream);
+void sdn_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDN_REPEL_H_ */

@@ -1,0 +1,179 @@
+// extern "C" entry points: argument checking, kernel-family dispatch, host-buffer convenience.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "sdn_internal.h"
+
+namespace sdn {
+std::atomic<uint64_t> g_launches{0};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t generic_workspace_bytes(int64_t Q, int64_t N) { return align_up(sizeof(float) * Q * N, 256); }
+
+static int pick_path(int32_t path, int64_t Q, int64_t N, int64_t D, const void* planes) {
+  if (path == SDN_PATH_AUTO) {
+    if (umma_supported(Q, N, D, planes) && Q > 8) return SDN_PATH_UMMA;
+    if (stream_supported(Q, N, D)) return SDN_PATH_STREAM;
+    return SDN_PATH_GENERIC;
+  }
+  return path;
+}
+}  // namespace sdn
+
+using namespace sdn;
+
+extern "C" {
+
+int sdn_abi_version(void) { return SDN_ABI_VERSION; }
+
+uint64_t sdn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* sdn_error_string(int code) {
+  switch (code) {
+    case SDN_OK: return "ok";
+    case SDN_E_NULL: return "required pointer is NULL";
+    case SDN_E_SHAPE: return "non-positive or inconsistent size";
+    case SDN_E_ALIGN: return "pointer not 16-byte aligned or D not a multiple of 4";
+    case SDN_E_PARAM: return "unsupported parameter value";
+    case SDN_E_WORKSPACE: return "workspace too small";
+    case SDN_E_UNSUPPORTED: return "shape not supported by the selected kernel family";
+    case SDN_E_DEVICE: return "device is not sm_100";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "unknown error";
+}
+
+size_t sdn_repel_workspace_bytes(int64_t Q, int64_t N, int64_t D, int32_t path) {
+  if (Q <= 0 || N <= 0 || D <= 0) return 0;
+  size_t need = generic_workspace_bytes(Q, N);
+  if (path == SDN_PATH_AUTO || path == SDN_PATH_STREAM) need = std::max(need, stream_workspace_bytes(Q, N, D));
+  if (path == SDN_PATH_AUTO || path == SDN_PATH_UMMA) need = std::max(need, umma_workspace_bytes(Q, N, D));
+  return need;
+}
+
+int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes, int64_t N, int64_t D,
+                      const float* xq, const float* xsq, int64_t Q, float inv_two_sigma_sq,
+                      int32_t dist_power, float bank_alpha, float* num_out, float* z_out, float* k_out,
+                      void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+  if (!sqnorm || !xq || !xsq || !z_out) return SDN_E_NULL;  // num_out NULL: z only (empirical_beta)
+  if (!bank && !planes) return SDN_E_NULL;
+  if (Q <= 0 || N <= 0 || D <= 0 || Q > 65535) return SDN_E_SHAPE;
+  if (dist_power != 1 && dist_power != 2) return SDN_E_PARAM;
+  if (D % 4 != 0 || (bank && !aligned16(bank)) || !aligned16(xq) || (num_out && !aligned16(num_out)))
+    return SDN_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chosen = num_out ? pick_path(path, Q, N, D, planes) : SDN_PATH_GENERIC;
+  switch (chosen) {
+    case SDN_PATH_STREAM:
+      if (!bank) return SDN_E_NULL;
+      if (!stream_supported(Q, N, D)) return SDN_E_UNSUPPORTED;
+      return stream_partial(bank, sqnorm, N, D, xq, xsq, Q, inv_two_sigma_sq, dist_power, bank_alpha,
+                            num_out, z_out, k_out, workspace, workspace_bytes, st);
+    case SDN_PATH_UMMA:
+      if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
+      return umma_partial(planes, sqnorm, N, D, xq, xsq, Q, inv_two_sigma_sq, dist_power, bank_alpha,
+                          num_out, z_out, k_out, workspace, workspace_bytes, st);
+    case SDN_PATH_GENERIC: break;
+    default: return SDN_E_PARAM;
+  }
+  if (!bank) return SDN_E_NULL;
+  float* S = k_out;
+  if (!S) {
+    if (!workspace || workspace_bytes < generic_workspace_bytes(Q, N)) return SDN_E_WORKSPACE;
+    S = static_cast<float*>(workspace);
+  }
+  int rc = generic_dots(bank, N, D, xq, Q, S, st);
+  if (rc) return rc;
+  rc = generic_weights(S, sqnorm, xsq, Q, N, inv_two_sigma_sq, dist_power, bank_alpha, z_out, st);
+  if (rc) return rc;
+  if (!num_out) return SDN_OK;
+  return generic_accum(bank, N, D, S, Q, num_out, st);
+}
+
+int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t D, float* x0_inout,
+                     const float* xsq, int64_t Q, float radius, float scale, float* term_out,
+                     float* wsum_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!bank || !sqnorm || !x0_inout || !xsq || !wsum_out || !workspace) return SDN_E_NULL;
+  if (Q <= 0 || N <= 0 || D <= 0 || Q > 65535) return SDN_E_SHAPE;
+  if (D % 4 != 0 || !aligned16(bank) || !aligned16(x0_inout) || (term_out && !aligned16(term_out)))
+    return SDN_E_ALIGN;
+  const size_t s_bytes = generic_workspace_bytes(Q, N);
+  const size_t need = s_bytes + align_up(sizeof(float) * Q * D, 256);
+  if (workspace_bytes < need) return SDN_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* S = static_cast<float*>(workspace);
+  float* num = reinterpret_cast<float*>(static_cast<char*>(workspace) + s_bytes);
+  int rc = generic_dots(bank, N, D, x0_inout, Q, S, st);
+  if (rc) return rc;
+  rc = sparse_weights(S, sqnorm, xsq, Q, N, radius, wsum_out, st);
+  if (rc) return rc;
+  rc = generic_accum(bank, N, D, S, Q, num, st);
+  if (rc) return rc;
+  return sparse_apply(num, wsum_out, Q, D, scale, x0_inout, term_out, st);
+}
+
+// ------------------------------------------------------------------ host-buffer path (e2e)
+namespace {
+struct HostCache {
+  std::mutex mu;
+  void* dev = nullptr;
+  size_t dev_bytes = 0;
+} g_host;
+}  // namespace
+
+void sdn_host_release(void) {
+  std::lock_guard<std::mutex> lk(g_host.mu);
+  if (g_host.dev) cudaFree(g_host.dev);
+  g_host.dev = nullptr;
+  g_host.dev_bytes = 0;
+}
+
+int sdn_conditioning_host(const float* bank, const float* sqnorm, const void* planes, int64_t N,
+                          int64_t D, float* x0_host, int64_t Q, int32_t normalize_C,
+                          float inv_two_sigma_sq, int32_t dist_power, float bank_alpha, float eps,
+                          float scale, float* denom_host, int32_t path, void* stream) {
+  if (!x0_host || !denom_host) return SDN_E_NULL;
+  if (Q <= 0 || N <= 0 || D <= 0) return SDN_E_SHAPE;
+  std::lock_guard<std::mutex> lk(g_host.mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t qd = align_up(sizeof(float) * Q * D, 256);
+  const size_t qv = align_up(sizeof(float) * Q, 256);
+  const size_t ws = align_up(sdn_repel_workspace_bytes(Q, N, D, path), 256);
+  // layout: x0 | xq | num | xsq | z | denom | workspace
+  const size_t need = 3 * qd + 3 * qv + ws;
+  if (need > g_host.dev_bytes) {
+    if (g_host.dev) SDN_CUDA_OK(cudaFree(g_host.dev));
+    g_host.dev = nullptr;
+    g_host.dev_bytes = 0;
+    SDN_CUDA_OK(cudaMalloc(&g_host.dev, need));
+    g_host.dev_bytes = need;
+  }
+  char* p = static_cast<char*>(g_host.dev);
+  float* x0 = reinterpret_cast<float*>(p);
+  float* xq = reinterpret_cast<float*>(p + qd);
+  float* num = reinterpret_cast<float*>(p + 2 * qd);
+  float* xsq = reinterpret_cast<float*>(p + 3 * qd);
+  float* z = reinterpret_cast<float*>(p + 3 * qd + qv);
+  float* denom = reinterpret_cast<float*>(p + 3 * qd + 2 * qv);
+  void* wsp = p + 3 * qd + 3 * qv;
+
+  SDN_CUDA_OK(cudaMemcpyAsync(x0, x0_host, sizeof(float) * Q * D, cudaMemcpyHostToDevice, st));
+  int rc = sdn_query_prepare(x0, nullptr, 1.f, 0.f, Q, D, normalize_C, nullptr,
+                             normalize_C > 0 ? xq : nullptr, xsq, stream);
+  if (rc) return rc;
+  const float* query = normalize_C > 0 ? xq : x0;
+  rc = sdn_repel_partial(bank, sqnorm, planes, N, D, query, xsq, Q, inv_two_sigma_sq, dist_power,
+                         bank_alpha, num, z, nullptr, wsp, ws, path, stream);
+  if (rc) return rc;
+  rc = sdn_epilogue_correct(num, z, Q, D, eps, scale, 0.f, 0, x0, nullptr, denom, nullptr, nullptr, stream);
+  if (rc) return rc;
+  SDN_CUDA_OK(cudaMemcpyAsync(x0_host, x0, sizeof(float) * Q * D, cudaMemcpyDeviceToHost, st));
+  SDN_CUDA_OK(cudaMemcpyAsync(denom_host, denom, sizeof(float) * Q, cudaMemcpyDeviceToHost, st));
+  SDN_CUDA_OK(cudaStreamSynchronize(st));
+  return SDN_OK;
+}
+
+}  // extern "C"

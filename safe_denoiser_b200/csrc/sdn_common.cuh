@@ -1,0 +1,73 @@
+// Shared helpers for the repellency-projection kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <atomic>
+
+#include "../../include/sdn_repel.h"
+
+namespace sdn {
+
+extern std::atomic<uint64_t> g_launches;
+
+#define SDN_CUDA_OK(expr)                                   \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) return static_cast<int>(_e);     \
+  } while (0)
+
+// Count the launch and surface launch-time errors as a positive cudaError_t.
+#define SDN_LAUNCHED()                                      \
+  do {                                                      \
+    ::sdn::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    cudaError_t _e = cudaGetLastError();                    \
+    if (_e != cudaSuccess) return static_cast<int>(_e);     \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in every thread.  `red` is >= 33 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Streaming 16-byte load that does not allocate in L1 (bank rows are read once per pass).
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// distance -> kernel weight, shared by every path (fast.py:249: exp(-cdist / (2 sigma^2))).
+__device__ __forceinline__ float dist_from_dot(float xsq, float nsq, float dot, float alpha, int power) {
+  float d2 = fmaf(-2.f * alpha, dot, fmaf(alpha * alpha, nsq, xsq));
+  d2 = fmaxf(d2, 0.f);
+  return power == 1 ? sqrtf(d2) : d2;
+}
+
+}  // namespace sdn

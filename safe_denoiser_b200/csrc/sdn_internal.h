@@ -1,0 +1,37 @@
+// Internal launch functions shared between translation units (not part of the C ABI).
+#pragma once
+#include "sdn_common.cuh"
+
+namespace sdn {
+
+// ---- generic CUDA-core two-phase path (sdn_generic.cu) ----
+// S[q,i] = xq_q . n_i
+int generic_dots(const float* bank, int64_t N, int64_t D, const float* xq, int64_t Q, float* S,
+                 cudaStream_t st);
+// in place: S[q,i] -> k_qi ; z[q] = sum_i k_qi   (deterministic, one block per row)
+int generic_weights(float* S, const float* sqnorm, const float* xsq, int64_t Q, int64_t N,
+                    float inv_two_sigma_sq, int power, float alpha, float* z, cudaStream_t st);
+// num[q,:] = sum_i k[q,i] n_i
+int generic_accum(const float* bank, int64_t N, int64_t D, const float* k, int64_t Q, float* num,
+                  cudaStream_t st);
+// in place: S[q,i] -> relu(radius / d_qi - 1) ; wsum[q] = sum_i of that   (SPELL)
+int sparse_weights(float* S, const float* sqnorm, const float* xsq, int64_t Q, int64_t N,
+                   float radius, float* wsum, cudaStream_t st);
+int sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale,
+                 float* x0_inout, float* term_out, cudaStream_t st);
+
+// ---- one-pass cluster path for GEMV-shaped calls (sdn_stream.cu) ----
+bool stream_supported(int64_t Q, int64_t N, int64_t D);
+size_t stream_workspace_bytes(int64_t Q, int64_t N, int64_t D);
+int stream_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                   const float* xsq, int64_t Q, float inv_two_sigma_sq, int power, float alpha,
+                   float* num, float* z, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// ---- tcgen05 two-phase path for batched calls (sdn_umma.cu) ----
+bool umma_supported(int64_t Q, int64_t N, int64_t D, const void* planes);
+size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D);
+int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                 const float* xsq, int64_t Q, float inv_two_sigma_sq, int power, float alpha,
+                 float* num, float* z, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace sdn

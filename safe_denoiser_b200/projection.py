@@ -1,0 +1,250 @@
+"""Host-side driver of the repellency projection: the prepared negative bank, the
+per-call scratch, and the three steps of one projection (query prepare ->
+partial sums over the bank -> fused epilogue), all through the C ABI.
+
+Reference behaviour replaced: RBFKernelRepellency.empirical_denoiser and
+RepellencyMethod.conditioning_1 (/root/reference/repellency/
+repellency_methods_fast.py:223-262, :129-132) and their sdv3 / threshold
+siblings.  The UNet / scheduler objects stay the caller's.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _native as nv
+
+
+class NegativeBank:
+    """The device-resident ``proj_ref`` tensor plus its derived data.
+
+    ``proj_refs`` is the [N,C,H,W] fp32 tensor of the reference's cache file
+    (fast.py:99-111).  Derived once here instead of on every call: ||n_i||^2
+    (torch.cdist recomputes it, fast.py:249) and, for the tcgen05 path, the
+    bf16 hi/lo planes.
+    """
+
+    def __init__(self, proj_refs: torch.Tensor, with_planes: bool = False):
+        if proj_refs.dim() < 2:
+            raise ValueError("bank must be [N, ...]")
+        if not proj_refs.is_cuda:
+            raise RuntimeError("NegativeBank needs a CUDA tensor; there is no CPU fallback")
+        t = proj_refs
+        if t.dtype != torch.float32:
+            t = t.float()
+        self.tensor = t.contiguous()
+        self.N = int(self.tensor.shape[0])
+        self.D = int(self.tensor[0].numel())
+        self.item_shape = tuple(self.tensor.shape[1:])
+        self.flat = self.tensor.view(self.N, self.D)
+        self.sqnorm = torch.empty(self.N, dtype=torch.float32, device=t.device)
+        self.planes = (torch.empty(2, self.N, self.D, dtype=torch.bfloat16, device=t.device)
+                       if with_planes else None)
+        nv.check(nv.lib().sdn_bank_prepare(nv.ptr(self.flat), self.N, self.D, nv.ptr(self.sqnorm),
+                                           nv.ptr(self.planes), nv.current_stream()))
+
+    @property
+    def device(self):
+        return self.tensor.device
+
+    def shard(self, rank: int, world: int) -> "NegativeBank":
+        """Contiguous N-shard [lo, hi) of this bank."""
+        lo, hi = shard_bounds(self.N, rank, world)
+        return NegativeBank(self.tensor[lo:hi], with_planes=self.planes is not None)
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Rows [lo, hi) of rank ``rank`` when n rows are split as evenly as possible."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class _Scratch:
+    __slots__ = ("num", "z", "xsq", "xq", "denom", "gate", "mean", "ws", "ws_bytes", "packed")
+
+
+class Projector:
+    """One bank + cached scratch; every method enqueues on the current stream and never syncs."""
+
+    def __init__(self, bank: NegativeBank, path: int = nv.PATH_AUTO, group=None):
+        self.bank = bank
+        self.path = path
+        self.group = group          # torch.distributed group for N-sharded banks (None = single GPU)
+        self._scratch = {}
+
+    # -- scratch -----------------------------------------------------------------------------
+    def _get(self, Q: int, need_xq: bool) -> _Scratch:
+        s = self._scratch.get(Q)
+        if s is None:
+            dev, D = self.bank.device, self.bank.D
+            s = _Scratch()
+            # num and z live in one packed [Q, D+1]-sized buffer so the N-shard merge is ONE all-reduce
+            s.packed = torch.empty(Q * D + Q, dtype=torch.float32, device=dev)
+            s.num = s.packed[: Q * D].view(Q, D)
+            s.z = s.packed[Q * D:]
+            s.xsq = torch.empty(Q, dtype=torch.float32, device=dev)
+            s.denom = torch.empty(Q, dtype=torch.float32, device=dev)
+            s.gate = torch.empty(Q, dtype=torch.int32, device=dev)
+            s.mean = torch.zeros(1, dtype=torch.float32, device=dev)
+            s.xq = None
+            s.ws_bytes = int(nv.lib().sdn_repel_workspace_bytes(Q, self.bank.N, D, self.path))
+            s.ws = torch.empty(max(s.ws_bytes, 16), dtype=torch.uint8, device=dev)
+            self._scratch[Q] = s
+        if need_xq and s.xq is None:
+            s.xq = torch.empty(Q, self.bank.D, dtype=torch.float32, device=self.bank.device)
+        return s
+
+    def _flat_query(self, x: torch.Tensor):
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise RuntimeError("query must be a CUDA fp32 tensor")
+        if not x.is_contiguous():
+            raise RuntimeError("query must be contiguous")
+        Q = int(x.shape[0])
+        if x[0].numel() != self.bank.D:
+            raise RuntimeError(
+                f"query rows have {x[0].numel()} elements but the bank rows have {self.bank.D}")
+        return Q, x.view(Q, self.bank.D)
+
+    # -- step 1+2: partial sums ----------------------------------------------------------------
+    def partial_sums(self, x0: torch.Tensor, sigma: float, *, normalize_channels: int = 0,
+                     model_out: torch.Tensor | None = None, c_x: float = 1.0, c_m: float = 0.0,
+                     x0_out: torch.Tensor | None = None, dist_power: int = 1, bank_alpha: float = 1.0,
+                     k_out: torch.Tensor | None = None, z_only: bool = False) -> _Scratch:
+        """num[Q,D] = sum_i k_qi n_i and z[Q] = sum_i k_qi over this (shard of the) bank, merged over
+        the process group when the bank is N-sharded.  ``x0`` contiguous fp32 [Q,...]."""
+        L = nv.lib()
+        st = nv.current_stream()
+        Q, xf = self._flat_query(x0)
+        s = self._get(Q, normalize_channels > 0)
+        mo = None
+        if model_out is not None:
+            mo = self._flat_query(model_out)[1]
+        xo = None if x0_out is None else self._flat_query(x0_out)[1]
+        nv.check(L.sdn_query_prepare(nv.ptr(xf), nv.ptr(mo), c_x, c_m, Q, self.bank.D,
+                                     int(normalize_channels), nv.ptr(xo), nv.ptr(s.xq) if normalize_channels > 0 else None,
+                                     nv.ptr(s.xsq), st))
+        if normalize_channels > 0:
+            query = s.xq
+        elif xo is not None:
+            query = xo
+        else:
+            query = xf
+        b = self.bank
+        nv.check(L.sdn_repel_partial(nv.ptr(b.flat), nv.ptr(b.sqnorm), nv.ptr(b.planes), b.N, b.D,
+                                     nv.ptr(query), nv.ptr(s.xsq), Q,
+                                     1.0 / (2.0 * float(sigma) ** 2), int(dist_power), float(bank_alpha),
+                                     None if z_only else nv.ptr(s.num), nv.ptr(s.z), nv.ptr(k_out),
+                                     nv.ptr(s.ws), s.ws_bytes, self.path, st))
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(s.z if z_only else s.packed, op=dist.ReduceOp.SUM, group=self.group)
+        return s
+
+    # -- step 3: epilogues ---------------------------------------------------------------------
+    def correct(self, x0: torch.Tensor, sigma: float, scale: float, eps: float, *,
+                normalize_channels: int = 0, gate_threshold: float | None = None,
+                want_neg: bool = False, apply: bool = True, dist_power: int = 1,
+                bank_alpha: float = 1.0, k_out: torch.Tensor | None = None):
+        """conditioning(): x0 <- x0 - scale * neg in place.  Returns (neg or None, scratch); scratch
+        holds denom [Q], gate [Q] (int32), mean [1] and num [Q,D] as device tensors."""
+        s = self.partial_sums(x0, sigma, normalize_channels=normalize_channels,
+                              dist_power=dist_power, bank_alpha=bank_alpha, k_out=k_out)
+        Q, xf = self._flat_query(x0)
+        neg = torch.empty_like(xf) if want_neg else None
+        s.mean.zero_()
+        flags = nv.EPI_GATE if gate_threshold is not None else 0
+        nv.check(nv.lib().sdn_epilogue_correct(
+            nv.ptr(s.num), nv.ptr(s.z), Q, self.bank.D, float(eps), float(scale),
+            float(gate_threshold if gate_threshold is not None else 0.0), flags,
+            nv.ptr(xf) if apply else None, nv.ptr(neg), nv.ptr(s.denom), nv.ptr(s.gate), nv.ptr(s.mean),
+            nv.current_stream()))
+        return neg, s
+
+    def ddpm_step(self, x_t, eps_pred, z1, z2, coeffs: dict, sigma: float, scale: float, eps: float, *,
+                  gate_threshold: float | None = None, return_neg: bool = False, ddim: bool = False,
+                  x0c_out: torch.Tensor | None = None):
+        """One fused in-window SD-1.4 step (...threshold_time.py:554-576): eps -> x0, projection,
+        correction, gate, re-noise and the scheduler update; no host sync.  ``coeffs`` as produced by
+        ``epilogue.ddpm_coefficients``.  Returns (latents, scratch)."""
+        sa, s1 = coeffs["sqrt_ab"], coeffs["sqrt_1m_ab"]
+        Q, xt = self._flat_query(x_t)
+        s0 = self._get(Q, True)
+        # x0 is only needed as the query: written to the xq scratch, never handed back
+        s = self.partial_sums(x_t, sigma, model_out=eps_pred, c_x=1.0 / sa, c_m=-s1 / sa, x0_out=s0.xq)
+        out = torch.empty_like(xt)
+        s.mean.zero_()
+        flags = (nv.EPI_GATE if gate_threshold is not None else 0) | (nv.EPI_RETURN_NEG if return_neg else 0)
+        thr = float(gate_threshold if gate_threshold is not None else 0.0)
+        L, st = nv.lib(), nv.current_stream()
+        e = self._flat_query(eps_pred)[1]
+        n1 = self._flat_query(z1)[1]
+        xc = None if x0c_out is None else self._flat_query(x0c_out)[1]
+        if ddim:
+            nv.check(L.sdn_epilogue_ddim(nv.ptr(s.num), nv.ptr(s.z), Q, self.bank.D, float(eps), float(scale),
+                                         thr, flags, nv.ptr(xt), nv.ptr(e), nv.ptr(n1), sa, s1,
+                                         coeffs["sqrt_ab_prev"], coeffs["sqrt_1m_ab_prev"],
+                                         nv.ptr(out), nv.ptr(xc), nv.ptr(s.denom), nv.ptr(s.gate),
+                                         nv.ptr(s.mean), st))
+        else:
+            n2 = None if z2 is None else self._flat_query(z2)[1]
+            nv.check(L.sdn_epilogue_ddpm(nv.ptr(s.num), nv.ptr(s.z), Q, self.bank.D, float(eps), float(scale),
+                                         thr, flags, nv.ptr(xt), nv.ptr(e), nv.ptr(n1), nv.ptr(n2), sa, s1,
+                                         coeffs["c_x0"], coeffs["c_xt"], coeffs["sigma_noise"],
+                                         nv.ptr(out), nv.ptr(xc), nv.ptr(s.denom), nv.ptr(s.gate),
+                                         nv.ptr(s.mean), st))
+        return out.view_as(x_t), s
+
+    def flow_step(self, x, v, zn, sigma_t: float, sigma_next: float, kernel_sigma: float, scale: float,
+                  eps: float, *, normalize_channels: int, x0c_out: torch.Tensor | None = None):
+        """One fused SD3 flow-matching step (safe_denoiser_pipeline.py:1142-1161).  fp32 in/out."""
+        Q, xf = self._flat_query(x)
+        s0 = self._get(Q, True)
+        x0_tmp = None if normalize_channels > 0 else s0.xq   # un-normalised x0 is only the query
+        s = self.partial_sums(x, kernel_sigma, normalize_channels=normalize_channels, model_out=v,
+                              c_x=1.0, c_m=-float(sigma_t), x0_out=x0_tmp)
+        out = torch.empty_like(xf)
+        s.mean.zero_()
+        xc = None if x0c_out is None else self._flat_query(x0c_out)[1]
+        nv.check(nv.lib().sdn_epilogue_flow(nv.ptr(s.num), nv.ptr(s.z), Q, self.bank.D, float(eps), float(scale),
+                                            nv.ptr(xf), nv.ptr(self._flat_query(v)[1]),
+                                            nv.ptr(self._flat_query(zn)[1]), float(sigma_t), float(sigma_next),
+                                            nv.ptr(out), nv.ptr(xc), nv.ptr(s.denom), nv.ptr(s.mean),
+                                            nv.current_stream()))
+        return out.view_as(x), s
+
+    def sparse(self, x0: torch.Tensor, radius: float, scale: float, want_term: bool = False):
+        """SPELL baseline (fast.py:306-340): x0 += scale * sum_i relu(radius/d_i - 1)(x0 - n_i) in place.
+        Returns (term or None, wsum [Q])."""
+        L, st = nv.lib(), nv.current_stream()
+        Q, xf = self._flat_query(x0)
+        s = self._get(Q, False)
+        b = self.bank
+        nv.check(L.sdn_query_prepare(nv.ptr(xf), None, 1.0, 0.0, Q, b.D, 0, None, None, nv.ptr(s.xsq), st))
+        need = Q * b.N * 4 + Q * b.D * 4 + 1024
+        ws = torch.empty(need, dtype=torch.uint8, device=b.device)
+        term = torch.empty_like(xf) if want_term else None
+        wsum = torch.empty(Q, dtype=torch.float32, device=b.device)
+        nv.check(L.sdn_sparse_repel(nv.ptr(b.flat), nv.ptr(b.sqnorm), b.N, b.D, nv.ptr(xf), nv.ptr(s.xsq), Q,
+                                    float(radius), float(scale), nv.ptr(term), nv.ptr(wsum),
+                                    nv.ptr(ws), need, st))
+        return term, wsum
+
+
+def conditioning_host(bank: NegativeBank, x0_host: torch.Tensor, denom_host: torch.Tensor, sigma: float,
+                      scale: float, eps: float = 1e-8, normalize_channels: int = 0, path: int = nv.PATH_AUTO):
+    """The e2e call: HOST query in, corrected HOST query out (in place), through the C ABI with the
+    host<->device copies inside the call."""
+    if x0_host.is_cuda or x0_host.dtype != torch.float32 or not x0_host.is_contiguous():
+        raise RuntimeError("x0_host must be a contiguous CPU fp32 tensor")
+    Q = int(x0_host.shape[0])
+    nv.check(nv.lib().sdn_conditioning_host(
+        nv.ptr(bank.flat), nv.ptr(bank.sqnorm), nv.ptr(bank.planes), bank.N, bank.D,
+        x0_host.data_ptr(), Q, int(normalize_channels), 1.0 / (2.0 * float(sigma) ** 2), 1, 1.0,
+        float(eps), float(scale), denom_host.data_ptr(), path, nv.current_stream()))
+    return x0_host
+
+
+def inv_two_sigma_sq(sigma: float) -> float:
+    return 1.0 / (2.0 * math.pow(float(sigma), 2))

@@ -1,0 +1,274 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference-made goldens.
+
+Tolerance (BASELINE.json north_star / SURVEY 8d): max rel err <= 1e-3 on the corrected x0 and on the
+weights w_i = k_i / (Z + eps), rel = ||a-b||_inf / ||b||_inf per tensor, plus an absolute floor of
+1e-30 for the all-underflow regime.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import repellency_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b, floor=1e-30):
+    a = np.asarray(a.detach().cpu().numpy() if torch.is_tensor(a) else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if torch.is_tensor(b) else b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), floor)
+
+
+@pytest.fixture(scope="module")
+def nv():
+    from safe_denoiser_b200 import _native
+    _native.lib()
+    return _native
+
+
+def available_paths(nv, Q, N, D):
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    paths = [nv.PATH_GENERIC]
+    bank = NegativeBank(torch.zeros(N, D, device="cuda") + 1.0, with_planes=True)
+    x = torch.ones(Q, D, device="cuda")
+    for p in (nv.PATH_STREAM, nv.PATH_UMMA):
+        try:
+            Projector(bank, path=p).partial_sums(x, 1.0)
+            paths.append(p)
+        except RuntimeError as e:
+            if "(-6)" not in str(e):
+                raise
+    torch.cuda.synchronize()
+    return paths
+
+
+def run_projection(nv, bank4, x4, sigma, scale, eps=1e-8, path=0, normalize=0, dist_power=1, alpha=1.0):
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    bank = NegativeBank(bank4.cuda(), with_planes=True)
+    proj = Projector(bank, path=path)
+    x = x4.cuda().contiguous().clone()
+    k = torch.empty(x.shape[0], bank.N, device="cuda")
+    neg, s = proj.correct(x, sigma, scale, eps, normalize_channels=normalize, want_neg=True,
+                          dist_power=dist_power, bank_alpha=alpha, k_out=k)
+    torch.cuda.synchronize()
+    w = k / s.denom[:, None]
+    return {"x0": x.cpu(), "neg": neg.cpu(), "denom": s.denom.cpu().clone(), "weights": w.cpu(),
+            "mean": float(s.mean.item()), "num": s.num.cpu().clone()}
+
+
+SHAPES = [  # (name, Q, N, C, H, W)
+    ("cfg1", 1, 515, 4, 64, 64),
+    ("cfg2", 16, 515, 4, 64, 64),
+    ("cfg3-small", 64, 384, 4, 64, 64),
+    ("ragged", 3, 37, 4, 8, 8),
+    ("one-negative", 2, 1, 4, 8, 8),
+    ("q5-n100", 5, 100, 4, 16, 16),
+]
+
+
+@pytest.mark.parametrize("name,Q,N,C,H,W", SHAPES)
+@pytest.mark.parametrize("regime", ["far", "x0", "near", "mid"])
+@pytest.mark.parametrize("sigma", [1.0, 3.15, 13.15])
+def test_projection_matches_oracle(nv, name, Q, N, C, H, W, regime, sigma):
+    if regime == "mid" and N < 2:
+        pytest.skip("needs two negatives")
+    bank = orc.synthetic_bank(N, C, H, W)
+    x = orc.synthetic_queries(bank, Q, regime)
+    want = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.33, sigma=sigma)
+    for path in available_paths(nv, Q, N, C * H * W):
+        got = run_projection(nv, bank, x, sigma, 0.33, path=path)
+        assert rel(got["x0"], want["x_0_hat"]) <= TOL, (path, "x0")
+        assert rel(got["weights"], want["weights"]) <= TOL, (path, "weights")
+        assert rel(got["denom"], want["denom"]) <= TOL, (path, "denom")
+        # the negative mean itself: relative to its own scale, with the underflow floor
+        assert rel(got["neg"], want["neg"], floor=1e-20) <= TOL or np.abs(want["neg"]).max() < 1e-20
+
+
+def test_cfg3_full_size(nv):
+    """BASELINE config 3 at full size: Q=64, N=3000, 4x64x64, near regime (non-trivial weights)."""
+    bank = orc.synthetic_bank(3000, 4, 64, 64)
+    x = orc.synthetic_queries(bank, 64, "near")
+    want = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.03, sigma=1.0)
+    got = run_projection(nv, bank, x, 1.0, 0.03)
+    assert rel(got["x0"], want["x_0_hat"]) <= TOL
+    assert rel(got["weights"], want["weights"]) <= TOL
+
+
+def test_sdv3_normalised_query(nv):
+    bank = orc.synthetic_bank(96, 16, 32, 32)
+    for regime in ("x0", "near"):
+        x = orc.synthetic_queries(bank, 4, regime)
+        want = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.03, sigma=1.0, sdv3=True)
+        got = run_projection(nv, bank, x, 1.0, 0.03, normalize=16)
+        assert rel(got["x0"], want["x_0_hat"]) <= TOL
+        assert rel(got["weights"], want["weights"]) <= TOL
+
+
+def test_squared_distance_and_alpha(nv):
+    bank = orc.synthetic_bank(50, 4, 8, 8)
+    x = orc.synthetic_queries(bank, 3, "near")
+    want = orc.closed_form(x.numpy(), bank.numpy(), sigma=2.0, dist_power=2, bank_alpha=0.8)
+    got = run_projection(nv, bank, x, 2.0, 0.0, dist_power=2, alpha=0.8)
+    assert rel(got["weights"], want["weights"]) <= TOL
+    assert rel(got["neg"], want["neg"].reshape(got["neg"].shape)) <= TOL
+
+
+# ---------------------------------------------------------------- goldens made by the reference
+def _module(kind):
+    import importlib
+    return importlib.import_module(f"safe_denoiser_b200.repellency.repellency_methods_{kind}")
+
+
+def _build(kind, name, bank, tmp_path, **params):
+    path = str(tmp_path / f"bank_{kind}_{name}.pt")
+    torch.save(torch.from_numpy(bank).clone(), path)
+    return _module(kind).get_repellency_method(
+        name, ref_data=torch.zeros(1, 3, 8, 8, device="cuda"), embed_fn=None, forward_fn=None,
+        num_timesteps=50, max_idx=1000, beta_min=0.00085, beta_max=0.012, n_embed=16,
+        proj_ref_path=path, cache_proj_ref=True, **params)
+
+
+@pytest.mark.parametrize("tag,kind", [("fast", "fast"), ("sdv3", "fast_sdv3")])
+def test_dropin_fast_against_reference_goldens(tag, kind, tmp_path):
+    fx = np.load(os.path.join(G, "fast_cases.npz"))
+    proc = _build(kind, "kernel_fast", fx[f"{tag}/bank"], tmp_path, scale=0.03, sigma=3.55)
+    for q in (1, 3):
+        for regime in ("far", "x0", "near", "mid"):
+            key = f"{tag}/q{q}/{regime}"
+            x = torch.from_numpy(fx[key + "/x"]).cuda()
+            neg, item = proc.empirical_denoiser(x_t=x.clone())
+            assert rel(neg, fx[key + "/neg"], floor=1e-20) <= TOL or np.abs(fx[key + "/neg"]).max() < 1e-20
+            xin = x.clone()
+            d = proc.conditioning(xin, beta_threshold=False)
+            assert d["x_0_hat"] is xin, "in-place contract (SURVEY Q8)"
+            assert rel(xin, fx[key + "/x0"]) <= TOL
+            assert abs(float(d["mean_x_0_hat"]) - float(fx[key + "/item"])) <= TOL * abs(float(fx[key + "/item"])) + 1e-12
+
+
+def test_dropin_threshold_against_reference_goldens(tmp_path):
+    fx = np.load(os.path.join(G, "threshold_cases.npz"))
+    for sigma in (3.15, 1.0, 13.15):
+        for regime in ("far", "x0", "near", "mid"):
+            key = f"thr/s{sigma}/{regime}"
+            sg, scale, thr, margin = [float(v) for v in fx[key + "/params"]]
+            proc = _build("threshold", "kernel_fast", fx["thr/bank"], tmp_path, scale=scale, sigma=sg,
+                          beta_threshold=thr, beta_threshold_margin=margin)
+            x = torch.from_numpy(fx[key + "/x"]).cuda()
+            xin = x.clone()
+            d = proc.conditioning(xin, beta_threshold=True)
+            assert d["x_0_hat"] is xin
+            assert rel(xin, fx[key + "/gate/x0"]) <= TOL
+            assert bool(d["is_negation"]) == bool(fx[key + "/gate/is_negation"])
+            assert abs(float(d["mean_x_0_hat"]["denominator"]) / float(fx[key + "/gate/denominator"]) - 1) <= TOL
+            assert rel(d["mean_x_0_hat"]["nominator"], fx[key + "/gate/nominator"]) <= TOL
+            xin = x.clone()
+            d = proc.conditioning(xin, beta_threshold=False)
+            assert rel(d["x_0_hat"], fx[key + "/nogate/x0"]) <= TOL          # negative mean (Q5)
+            assert rel(xin, fx[key + "/nogate/x_inplace"]) <= TOL
+            assert d["is_negation"] is True
+
+
+def test_dropin_sparse_against_reference_goldens(tmp_path):
+    fx = np.load(os.path.join(G, "sparse_cases.npz"))
+    for tag, kind in (("fast", "fast"), ("thr", "threshold")):
+        for radius in (4.0, 11.5, 13.0):
+            proc = _build(kind, "sparse", fx["sparse/bank"], tmp_path, scale=1.6, radius=radius)
+            for regime in ("near", "x0", "mid"):
+                key = f"sparse/{tag}/r{radius}/{regime}"
+                xin = torch.from_numpy(fx[key + "/x"]).cuda()
+                d = proc.conditioning(xin, beta_threshold=False)
+                assert rel(xin, fx[key + "/x0"]) <= TOL, key
+                want = float(fx[key + "/item"])
+                assert abs(float(d["mean_x_0_hat"]) - want) <= 2e-3 * max(1.0, want)
+                if tag == "thr":
+                    assert bool(d["is_negation"]) == bool(fx[key + "/is_negation"])
+
+
+def test_empirical_beta_against_reference_goldens(tmp_path):
+    fx = np.load(os.path.join(G, "beta_cases.npz"))
+    proc = _build("threshold", "kernel_fast", fx["beta/bank"], tmp_path, scale=0.33, sigma=3.15,
+                  beta_threshold=1.0)
+    ts = [int(t) for t in fx["beta/timesteps"]]
+    proc.noisy_proj_refs = {t: torch.from_numpy(fx[f"beta/noisy/{t}"]).cuda() for t in ts}
+    for qt in (0.0, 0.25):
+        got = proc.empirical_beta(sigma=3.15, quantitle=qt, rows_per_call=16)
+        np.testing.assert_allclose([float(got[t]) for t in ts], fx[f"beta/q{qt}"], rtol=TOL)
+
+
+def test_auto_beta_construction(tmp_path):
+    """kernel_fast with no beta_threshold calibrates it from the noisy bank (threshold.py:291-306)."""
+    fx = np.load(os.path.join(G, "beta_cases.npz"))
+    ts = [int(t) for t in fx["beta/timesteps"]]
+    noisy_path = str(tmp_path / "noisy.pt")
+    torch.save({t: torch.from_numpy(fx[f"beta/noisy/{t}"]) for t in ts}, noisy_path)
+    proc = _build("threshold", "kernel_fast", fx["beta/bank"], tmp_path, scale=0.33, sigma=3.15,
+                  proj_noisy_ref_path_for_beta=noisy_path, cache_noisy_ref_path_for_beta=True)
+    assert abs(float(proc.beta_threshold) / fx["beta/q0.0"][-1] - 1) <= TOL
+
+
+# ---------------------------------------------------------------- properties at full size
+def test_shard_additivity_full_size(nv):
+    """sum of per-shard partial sums == full-bank sums (the N-shard merge is exact up to fp32 order)."""
+    from safe_denoiser_b200.projection import NegativeBank, Projector, shard_bounds
+    bank4 = orc.synthetic_bank(3000, 4, 64, 64).cuda()
+    x = orc.synthetic_queries(bank4.cpu(), 8, "near").cuda()
+    full = Projector(NegativeBank(bank4)).partial_sums(x, 3.15)
+    num, z = full.num.clone(), full.z.clone()
+    acc_n, acc_z = torch.zeros_like(num), torch.zeros_like(z)
+    for r in range(8):
+        lo, hi = shard_bounds(3000, r, 8)
+        s = Projector(NegativeBank(bank4[lo:hi])).partial_sums(x, 3.15)
+        acc_n += s.num
+        acc_z += s.z
+    assert rel(acc_n, num) <= 1e-5
+    assert rel(acc_z, z) <= 1e-5
+
+
+def test_duplicated_bank_keeps_negative_mean(nv):
+    bank = orc.synthetic_bank(200, 4, 64, 64)
+    x = orc.synthetic_queries(bank, 4, "near")
+    a = run_projection(nv, bank, x, 3.15, 0.33, eps=0.0)
+    b = run_projection(nv, torch.cat([bank, bank]), x, 3.15, 0.33, eps=0.0)
+    assert rel(b["denom"], 2 * a["denom"].numpy()) <= 1e-5
+    assert rel(b["neg"], a["neg"]) <= 1e-5
+
+
+def test_query_equal_to_a_negative(nv):
+    """d = 0 for one pair: weight exp(0) = 1 dominates; clamp keeps sqrt of a tiny negative finite."""
+    bank = orc.synthetic_bank(64, 4, 32, 32)
+    x = bank[5:6].clone()
+    want = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.5, sigma=1.0)
+    got = run_projection(nv, bank, x, 1.0, 0.5)
+    assert torch.isfinite(got["x0"]).all()
+    assert rel(got["x0"], want["x_0_hat"]) <= 5e-3   # sqrt amplifies fp32 cancellation at d ~ 0 (reference has the same noise)
+
+
+def test_host_call_matches_device_call(nv):
+    from safe_denoiser_b200.projection import NegativeBank, conditioning_host
+    bank4 = orc.synthetic_bank(515, 4, 64, 64)
+    x = orc.synthetic_queries(bank4, 4, "near")
+    dev = run_projection(nv, bank4, x, 3.15, 0.33)
+    bank = NegativeBank(bank4.cuda())
+    xh = x.clone().contiguous().pin_memory()
+    dh = torch.empty(4).pin_memory()
+    conditioning_host(bank, xh, dh, 3.15, 0.33)
+    assert rel(xh, dev["x0"]) <= 1e-6
+    assert rel(dh, dev["denom"]) <= 1e-6
+
+
+def test_errors_are_loud(nv):
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    bank = NegativeBank(orc.synthetic_bank(10, 4, 8, 8).cuda())
+    with pytest.raises(RuntimeError):
+        Projector(bank).partial_sums(torch.zeros(1, 4, 8, 9, device="cuda"), 1.0)   # shape mismatch
+    with pytest.raises(RuntimeError):
+        Projector(bank).partial_sums(torch.zeros(1, 4, 8, 8), 1.0)                  # CPU tensor
+    L = nv.lib()
+    assert L.sdn_repel_partial(None, None, None, 1, 4, None, None, 1, 1.0, 1, 1.0, None, None, None, None, 0, 0, None) == -1
+    assert L.sdn_bank_prepare(bank.flat.data_ptr(), 0, 256, bank.sqnorm.data_ptr(), None, None) == -2
+    assert L.sdn_bank_prepare(bank.flat.data_ptr() + 4, 10, 256, bank.sqnorm.data_ptr(), None, None) == -3
