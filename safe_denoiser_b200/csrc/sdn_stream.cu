@@ -1,11 +1,418 @@
-// One-pass cluster kernel for GEMV-shaped calls (small Q).  Filled in below the generic path.
+// One-pass "flash-repellency" kernel for GEMV-shaped calls (Q <= 8): the bank is read from HBM ONCE.
+//
+// A thread-block cluster of CS CTAs owns a contiguous range of bank rows; CTA r of the cluster owns the
+// D-slice [r*SLICE, (r+1)*SLICE) of every row (SLICE = D / CS floats).  Rows stream through a ring of
+// shared-memory stages filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx).  Per tile of TN rows:
+//
+//   phase 1   partial dots x_q[slice] . n_i[slice] from smem -> warp reduce-scatter -> CTA partial
+//             -> scattered into every peer CTA's receive buffer through distributed shared memory
+//             -> barrier.cluster.arrive            (split-phase: the wait comes after phase 2)
+//   phase 2   (for the PREVIOUS tile, whose partials have all arrived)  full dot -> distance -> k = exp(.)
+//             -> acc[q][slice] += k * n_i[slice]   re-reading the SAME smem tile: no second HBM pass
+//   barrier.cluster.wait
+//
+// The accumulators (Q x SLICE per CTA) and the query slice live in registers.  Each cluster writes one
+// partial [Q, D] (+ Z[Q]); a small second kernel sums the per-cluster partials (deterministic).
+//
+// Replaces repellency_methods_fast.py:249-257 for the shapes the reference actually runs (Q = 1).
+#include <algorithm>
+
 #include "sdn_internal.h"
 
 namespace sdn {
-bool stream_supported(int64_t, int64_t, int64_t) { return false; }
-size_t stream_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-int stream_partial(const float*, const float*, int64_t, int64_t, const float*, const float*, int64_t, float,
-                   int, float, float*, float*, float*, void*, size_t, cudaStream_t) {
-  return SDN_E_UNSUPPORTED;
+
+constexpr int kStThreads = 512;
+constexpr int kStWarps = kStThreads / 32;
+constexpr int kStStages = 6;
+constexpr int kStMaxCluster = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a broken pipeline traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_remote(float* local_addr, uint32_t peer, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_addr)), "r"(peer));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+// Sum V per-lane values across the warp with a reduce-scatter butterfly (V-1 shuffles instead of 5V).
+// On return, lane l holds in v[0] the warp total of value index `warp_value_index<V>(l)`.
+template <int V>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[V], int lane) {
+  static_assert(V == 1 || V == 2 || V == 4 || V == 8 || V == 16 || V == 32, "V must be a power of two <= 32");
+  int off = 16;
+#pragma unroll
+  for (int n = V; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+    const int h = n >> 1;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = upper ? v[i] : v[i + h];
+      const float keep = upper ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+// Which value index lane `lane` ends up holding: step j (offset 16 >> j) picks the upper half when the
+// lane bit is set, so the index accumulates bit (log2V-1-j) from lane bit (4-j).
+template <int V>
+__device__ __forceinline__ int warp_value_index(int lane) {
+  int idx = 0, off = 16;
+#pragma unroll
+  for (int n = V; n > 1; n >>= 1, off >>= 1)
+    if (lane & off) idx += n >> 1;
+  return idx;
+}
+// Lanes that hold a distinct value: those whose low (5 - log2 V) bits are zero.
+template <int V>
+__device__ __forceinline__ bool warp_value_owner(int lane) {
+  int bits = 0;
+  for (int n = V; n > 1; n >>= 1) ++bits;
+  return (lane & ((1 << (5 - bits)) - 1)) == 0;
+}
+
+struct StreamArgs {
+  const float* bank; const float* sqnorm; int64_t N; int64_t D;
+  const float* x; const float* xsq; int q_real;
+  float inv2s2; int power; float alpha;
+  float* part_num;   // [clusters][q_real][D]
+  float* part_z;     // [clusters][q_real]
+  float* k_out;      // [q_real][N] or null
+};
+
+template <int Q, int VPT, int TN>
+constexpr size_t stream_smem_bytes() {
+  constexpr size_t slice = (size_t)VPT * kStThreads * 4;
+  constexpr size_t V = (size_t)TN * Q;
+  return kStStages * TN * slice * 4        // tile ring
+         + kStWarps * V * 4                // per-warp partials
+         + 3 * kStMaxCluster * V * 4       // receive slots
+         + V * 4                           // k of the tile being accumulated
+         + 64 * 4                          // z reduction scratch
+         + kStStages * 8 + 64;             // mbarriers + alignment slack
+}
+
+template <int Q, int VPT, int TN>
+__global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
+  constexpr int V = TN * Q;
+  constexpr int SLICE = VPT * kStThreads * 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tiles = reinterpret_cast<float*>(smem_raw);                 // [stages][TN][SLICE]
+  float* wp = tiles + (size_t)kStStages * TN * SLICE;                 // [warps][V]
+  float* recv = wp + kStWarps * V;                                    // [3][kStMaxCluster][V]
+  float* ks = recv + 3 * kStMaxCluster * V;                           // [V]
+  float* zred = ks + V;                                               // [64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(zred + 64);            // [stages]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t crank = cluster_rank(), csize = cluster_size();
+  const int cid = blockIdx.x / csize, ncl = gridDim.x / csize;
+
+  // rows of this cluster: as even as possible
+  const int64_t base = a.N / ncl, rem = a.N % ncl;
+  const int64_t lo = cid * base + min<int64_t>(cid, rem);
+  const int64_t hi = lo + base + (cid < rem ? 1 : 0);
+  const int ntiles = (int)((hi - lo + TN - 1) / TN);
+  const float* slice0 = a.bank + (int64_t)crank * SLICE;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int tt) {   // thread 0 only
+    const int s = tt % kStStages;
+    const int64_t r0 = lo + (int64_t)tt * TN;
+    const int rows = (int)min<int64_t>(TN, hi - r0);
+    mbar_expect_tx(&full[s], (uint32_t)(rows * SLICE * 4));
+    for (int r = 0; r < rows; ++r)
+      bulk_g2s(tiles + ((size_t)s * TN + r) * SLICE, slice0 + (r0 + r) * a.D, SLICE * 4, &full[s]);
+  };
+  if (tid == 0)
+    for (int tt = 0; tt < min(ntiles, kStStages - 2); ++tt) issue(tt);
+
+  // query slice and accumulators in registers: thread owns floats [v*kStThreads*4 + tid*4, +4) of the slice
+  float4 xr[Q][VPT], acc[Q][VPT];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int qs = min(q, a.q_real - 1);
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      xr[q][v] = *reinterpret_cast<const float4*>(a.x + (int64_t)qs * a.D + (int64_t)crank * SLICE +
+                                                  (v * kStThreads + tid) * 4);
+      acc[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float zacc = 0.f;            // threads < V: sum of k for (row slot tid / Q, query tid % Q)
+  float xs_q = 0.f;
+  if (tid < V) xs_q = a.xsq[min(tid % Q, a.q_real - 1)];
+  float nsq_prev = 0.f;        // sqnorm of the row this thread finalises in phase 2 (loaded one tile ahead)
+
+  // all CTAs of the cluster must have started (their smem must exist) before the first remote store
+  cluster_arrive();
+  cluster_wait();
+
+  for (int t = 0; t <= ntiles; ++t) {
+    float nsq_cur = 0.f;
+    if (t < ntiles) {
+      // ---------------- phase 1: partial dots of tile t ----------------
+      const int s = t % kStStages;
+      const int64_t r0 = lo + (int64_t)t * TN;
+      const int rows = (int)min<int64_t>(TN, hi - r0);
+      if (tid < V && tid / Q < rows) nsq_cur = a.sqnorm[r0 + tid / Q];
+      mbar_wait(&full[s], (uint32_t)((t / kStStages) & 1));
+      float part[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) part[i] = 0.f;
+      const float* tile = tiles + (size_t)s * TN * SLICE;
+#pragma unroll
+      for (int r = 0; r < TN; ++r) {
+        if (r < rows) {
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) {
+            const float4 b = *reinterpret_cast<const float4*>(tile + (size_t)r * SLICE + (v * kStThreads + tid) * 4);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              float p = part[r * Q + q];
+              p = fmaf(b.x, xr[q][v].x, p);
+              p = fmaf(b.y, xr[q][v].y, p);
+              p = fmaf(b.z, xr[q][v].z, p);
+              p = fmaf(b.w, xr[q][v].w, p);
+              part[r * Q + q] = p;
+            }
+          }
+        }
+      }
+      warp_reduce_scatter<V>(part, lane);
+      if (warp_value_owner<V>(lane)) wp[warp * V + warp_value_index<V>(lane)] = part[0];
+    }
+    __syncthreads();   // A_t: warp partials visible; every thread is done accumulating tile t-2
+    if (tid == 0 && t + kStStages - 2 < ntiles) issue(t + kStStages - 2);
+    if (t < ntiles && tid < V) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kStWarps; ++w) sum += wp[w * V + tid];
+      float* slot = recv + ((size_t)(t % 3) * kStMaxCluster + crank) * V + tid;
+      for (uint32_t peer = 0; peer < csize; ++peer) st_remote(slot, peer, sum);
+    }
+    cluster_arrive();
+
+    if (t > 0) {
+      // ---------------- phase 2: finish tile t-1 ----------------
+      const int tp = t - 1;
+      const int s = tp % kStStages;
+      const int64_t r0 = lo + (int64_t)tp * TN;
+      const int rows = (int)min<int64_t>(TN, hi - r0);
+      if (tid < V) {
+        const int r = tid / Q, q = tid % Q;
+        float k = 0.f;
+        if (r < rows) {
+          float dot = 0.f;
+          const float* slot = recv + (size_t)(tp % 3) * kStMaxCluster * V + tid;
+          for (uint32_t src = 0; src < csize; ++src) dot += slot[src * V];
+          const float d = dist_from_dot(xs_q, nsq_prev, dot, a.alpha, a.power);
+          k = expf(-d * a.inv2s2);
+          if (crank == 0 && a.k_out && q < a.q_real) a.k_out[(int64_t)q * a.N + r0 + r] = k;
+        }
+        ks[tid] = k;
+        zacc += k;
+      }
+      __syncthreads();   // B_t
+      const float* tile = tiles + (size_t)s * TN * SLICE;
+#pragma unroll
+      for (int r = 0; r < TN; ++r) {
+        if (r < rows) {
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) {
+            const float4 b = *reinterpret_cast<const float4*>(tile + (size_t)r * SLICE + (v * kStThreads + tid) * 4);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              const float k = ks[r * Q + q];
+              acc[q][v].x = fmaf(k, b.x, acc[q][v].x);
+              acc[q][v].y = fmaf(k, b.y, acc[q][v].y);
+              acc[q][v].z = fmaf(k, b.z, acc[q][v].z);
+              acc[q][v].w = fmaf(k, b.w, acc[q][v].w);
+            }
+          }
+        }
+      }
+    }
+    nsq_prev = nsq_cur;
+    cluster_wait();
+  }
+
+  // ---------------- write this cluster's partial sums ----------------
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    if (q < a.q_real) {
+#pragma unroll
+      for (int v = 0; v < VPT; ++v)
+        *reinterpret_cast<float4*>(a.part_num + ((int64_t)cid * a.q_real + q) * a.D + (int64_t)crank * SLICE +
+                                   (v * kStThreads + tid) * 4) = acc[q][v];
+    }
+  }
+  if (crank == 0) {
+    __syncthreads();
+    if (tid < 64) zred[tid] = (tid < V) ? zacc : 0.f;
+    __syncthreads();
+    if (tid < Q && tid < a.q_real) {
+      float z = 0.f;
+      for (int r = 0; r < TN; ++r) z += zred[r * Q + tid];
+      a.part_z[(int64_t)cid * a.q_real + tid] = z;
+    }
+  }
+  // no CTA may exit while a peer can still write into its shared memory
+  cluster_arrive();
+  cluster_wait();
+}
+
+// num[q][d] = sum_c part[c][q][d] ; z[q] = sum_c part_z[c][q]
+__global__ void __launch_bounds__(256)
+k_stream_reduce(const float* __restrict__ part_num, const float* __restrict__ part_z, int ncl, int64_t QD,
+                int Q, float* __restrict__ num, float* __restrict__ z) {
+  const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (j < QD) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < ncl; ++c) {
+      const float4 p = *reinterpret_cast<const float4*>(part_num + (int64_t)c * QD + j);
+      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    *reinterpret_cast<float4*>(num + j) = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < Q) {
+    float s = 0.f;
+    for (int c = 0; c < ncl; ++c) s += part_z[(int64_t)c * Q + threadIdx.x];
+    z[threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct StreamPlan {
+  int qt = 0, vpt = 0, tn = 0, cs = 0;   // template instance and cluster size
+  bool ok = false;
+};
+
+static StreamPlan plan_stream(int64_t Q, int64_t N, int64_t D) {
+  StreamPlan p;
+  if (Q < 1 || Q > 8 || N < 1) return p;
+  p.qt = Q <= 1 ? 1 : (Q <= 2 ? 2 : (Q <= 4 ? 4 : 8));
+  // slice = vpt * 2048 floats, cluster size = D / slice must be a power of two in [1, 8]
+  for (int vpt : {1, 2, 4}) {
+    if (vpt > 1 && p.qt * vpt > 8) continue;
+    const int64_t slice = (int64_t)vpt * kStThreads * 4;
+    if (D % slice) continue;
+    const int64_t cs = D / slice;
+    if (cs < 1 || cs > 8 || (cs & (cs - 1))) continue;
+    p.vpt = vpt;
+    p.cs = (int)cs;
+    p.tn = vpt == 1 ? (p.qt == 8 ? 2 : 4) : (vpt == 2 ? 2 : 1);
+    p.ok = true;
+    return p;
+  }
+  return p;
+}
+
+template <int Q, int VPT, int TN>
+static int launch_stream_t(const StreamArgs& a, int cs, int max_clusters_hint, int* ncl_out, cudaStream_t st) {
+  auto kern = k_stream<Q, VPT, TN>;
+  constexpr size_t smem = stream_smem_bytes<Q, VPT, TN>();
+  static bool configured = false;
+  static int max_clusters = 0;
+  if (!configured) {
+    SDN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t probe{};
+    probe.gridDim = dim3(kNumSMs / cs * cs);
+    probe.blockDim = dim3(kStThreads);
+    probe.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    probe.attrs = at; probe.numAttrs = 1;
+    int n = 0;
+    SDN_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &probe));
+    max_clusters = std::max(1, n);
+    configured = true;
+  }
+  int ncl = std::min(max_clusters, max_clusters_hint);
+  ncl = (int)std::min<int64_t>(ncl, std::max<int64_t>(1, cdiv(a.N, TN)));
+  *ncl_out = ncl;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ncl * cs);
+  cfg.blockDim = dim3(kStThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  SDN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
+  SDN_LAUNCHED();
+  return SDN_OK;
+}
+
+static int max_clusters_for(int cs) { return kNumSMs / cs; }
+
+bool stream_supported(int64_t Q, int64_t N, int64_t D) { return plan_stream(Q, N, D).ok; }
+
+size_t stream_workspace_bytes(int64_t Q, int64_t N, int64_t D) {
+  const StreamPlan p = plan_stream(Q, N, D);
+  if (!p.ok) return 0;
+  const size_t ncl = max_clusters_for(p.cs);
+  return ncl * (size_t)Q * D * 4 + ncl * (size_t)Q * 4 + 256;
+}
+
+int stream_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                   const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
+                   float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const StreamPlan p = plan_stream(Q, N, D);
+  if (!p.ok) return SDN_E_UNSUPPORTED;
+  if (!ws || ws_bytes < stream_workspace_bytes(Q, N, D)) return SDN_E_WORKSPACE;
+  const int hint = max_clusters_for(p.cs);
+  StreamArgs a{};
+  a.bank = bank; a.sqnorm = sqnorm; a.N = N; a.D = D; a.x = xq; a.xsq = xsq; a.q_real = (int)Q;
+  a.inv2s2 = inv2s2; a.power = power; a.alpha = alpha; a.k_out = k_out;
+  a.part_num = static_cast<float*>(ws);
+  a.part_z = a.part_num + (size_t)hint * Q * D;
+  int ncl = 0, rc = SDN_E_UNSUPPORTED;
+#define SDN_ST_CASE(QQ, VV, TT) \
+  if (p.qt == QQ && p.vpt == VV && p.tn == TT) rc = launch_stream_t<QQ, VV, TT>(a, p.cs, hint, &ncl, st);
+  SDN_ST_CASE(1, 1, 4) SDN_ST_CASE(2, 1, 4) SDN_ST_CASE(4, 1, 4) SDN_ST_CASE(8, 1, 2)
+  SDN_ST_CASE(1, 2, 2) SDN_ST_CASE(2, 2, 2) SDN_ST_CASE(4, 2, 2)
+  SDN_ST_CASE(1, 4, 1) SDN_ST_CASE(2, 4, 1)
+#undef SDN_ST_CASE
+  if (rc) return rc;
+  const int64_t QD = Q * D;
+  k_stream_reduce<<<(unsigned)cdiv(QD, 1024), 256, 0, st>>>(a.part_num, a.part_z, ncl, QD, (int)Q, num, z);
+  SDN_LAUNCHED();
+  return SDN_OK;
+}
+
 }  // namespace sdn

@@ -21,6 +21,9 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 def rel(a, b, floor=1e-30):
     a = np.asarray(a.detach().cpu().numpy() if torch.is_tensor(a) else a, np.float64)
     b = np.asarray(b.detach().cpu().numpy() if torch.is_tensor(b) else b, np.float64)
+    if a.shape != b.shape:
+        assert a.size == b.size, (a.shape, b.shape)
+        a = a.reshape(b.shape)
     return np.abs(a - b).max() / max(np.abs(b).max(), floor)
 
 
@@ -31,7 +34,16 @@ def nv():
     return _native
 
 
+_PATHS = {}
+
+
 def available_paths(nv, Q, N, D):
+    if (Q, N, D) not in _PATHS:
+        _PATHS[(Q, N, D)] = _probe_paths(nv, Q, N, D)
+    return _PATHS[(Q, N, D)]
+
+
+def _probe_paths(nv, Q, N, D):
     from safe_denoiser_b200.projection import NegativeBank, Projector
     paths = [nv.PATH_GENERIC]
     bank = NegativeBank(torch.zeros(N, D, device="cuda") + 1.0, with_planes=True)
