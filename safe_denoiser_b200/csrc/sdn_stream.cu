@@ -5,24 +5,25 @@
 // shared-memory stages filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx).  Per tile of TN rows:
 //
 //   phase 1   partial dots x_q[slice] . n_i[slice] from smem -> warp reduce-scatter -> CTA partial
-//             -> scattered into every peer CTA's receive buffer through distributed shared memory
-//             -> barrier.cluster.arrive            (split-phase: the wait comes after phase 2)
+//             -> st.async into every peer CTA's receive slot through distributed shared memory; each
+//                store completes bytes on the RECEIVER's mbarrier (no cluster barrier, no fence)
 //   phase 2   (for the PREVIOUS tile, whose partials have all arrived)  full dot -> distance -> k = exp(.)
 //             -> acc[q][slice] += k * n_i[slice]   re-reading the SAME smem tile: no second HBM pass
-//   barrier.cluster.wait
 //
 // The accumulators (Q x SLICE per CTA) and the query slice live in registers.  Each cluster writes one
 // partial [Q, D] (+ Z[Q]); a small second kernel sums the per-cluster partials (deterministic).
 //
 // Replaces repellency_methods_fast.py:249-257 for the shapes the reference actually runs (Q = 1).
 #include <algorithm>
+#include <cstdlib>
 
 #include "sdn_internal.h"
 
 namespace sdn {
 
-constexpr int kStThreads = 512;
-constexpr int kStWarps = kStThreads / 32;
+constexpr int kStCompute = 512;               // compute threads
+constexpr int kStCWarps = kStCompute / 32;    // 16 compute warps
+constexpr int kStThreads = kStCompute + 64;   // + TMA producer warp + weights warp
 constexpr int kStStages = 6;
 constexpr int kStMaxCluster = 16;
 
@@ -30,6 +31,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -54,10 +58,13 @@ __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("m
 __device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void st_remote(float* local_addr, uint32_t peer, float v) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_addr)), "r"(peer));
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+// Store one float into CTA `peer`'s copy of `local_addr` and complete 4 bytes on that CTA's copy of `local_bar`.
+__device__ __forceinline__ void st_async_remote(float* local_addr, uint64_t* local_bar, uint32_t peer, float v) {
+  uint32_t raddr, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_addr)), "r"(peer));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(peer));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
 }
 
 // Sum V per-lane values across the warp with a reduce-scatter butterfly (V-1 shuffles instead of 5V).
@@ -109,27 +116,33 @@ struct StreamArgs {
 
 template <int Q, int VPT, int TN>
 constexpr size_t stream_smem_bytes() {
-  constexpr size_t slice = (size_t)VPT * kStThreads * 4;
+  constexpr size_t slice = (size_t)VPT * kStCompute * 4;
   constexpr size_t V = (size_t)TN * Q;
-  return kStStages * TN * slice * 4        // tile ring
-         + kStWarps * V * 4                // per-warp partials
-         + 3 * kStMaxCluster * V * 4       // receive slots
-         + V * 4                           // k of the tile being accumulated
-         + 64 * 4                          // z reduction scratch
-         + kStStages * 8 + 64;             // mbarriers + alignment slack
+  return kStStages * TN * slice * 4          // tile ring
+         + 2 * kStCWarps * V * 4             // per-warp partials, double buffered
+         + 3 * kStMaxCluster * V * 4         // receive slots
+         + 2 * V * 4                         // k of the tiles being accumulated, double buffered
+         + 64 * 4                            // z reduction scratch
+         + (2 * kStStages + 2 + 2 + 3) * 8 + 64;   // mbarriers + alignment slack
 }
 
+// Warp roles: warps [0, 16) compute, warp 16 lane 0 issues the TMA bulk copies, warp 17 lanes [0, V) turn
+// partial dots into weights.  All hand-offs are mbarriers; there is no __syncthreads in the loop.
 template <int Q, int VPT, int TN>
 __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
   constexpr int V = TN * Q;
-  constexpr int SLICE = VPT * kStThreads * 4;
+  constexpr int SLICE = VPT * kStCompute * 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tiles = reinterpret_cast<float*>(smem_raw);                 // [stages][TN][SLICE]
-  float* wp = tiles + (size_t)kStStages * TN * SLICE;                 // [warps][V]
-  float* recv = wp + kStWarps * V;                                    // [3][kStMaxCluster][V]
-  float* ks = recv + 3 * kStMaxCluster * V;                           // [V]
-  float* zred = ks + V;                                               // [64]
-  uint64_t* full = reinterpret_cast<uint64_t*>(zred + 64);            // [stages]
+  float* wp = tiles + (size_t)kStStages * TN * SLICE;                 // [2][cwarps][V]
+  float* recv = wp + 2 * kStCWarps * V;                               // [3][kStMaxCluster][V]
+  float* ks = recv + 3 * kStMaxCluster * V;                           // [2][V]
+  float* zred = ks + 2 * V;                                           // [64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(zred + 64);            // [stages]  TMA landed
+  uint64_t* empty = full + kStStages;                                 // [stages]  all compute warps done with the stage
+  uint64_t* pr = empty + kStStages;                                   // [2]       warp partials of a tile written
+  uint64_t* kr = pr + 2;                                              // [2]       weights of a tile written
+  uint64_t* rbar = kr + 2;                                            // [3]       peers' partials landed
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t crank = cluster_rank(), csize = cluster_size();
@@ -137,180 +150,200 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
 
   // rows of this cluster: as even as possible
   const int64_t base = a.N / ncl, rem = a.N % ncl;
-  const int64_t lo = cid * base + min<int64_t>(cid, rem);
+  const int64_t lo = cid * base + min((int64_t)cid, rem);
   const int64_t hi = lo + base + (cid < rem ? 1 : 0);
   const int ntiles = (int)((hi - lo + TN - 1) / TN);
-  const float* slice0 = a.bank + (int64_t)crank * SLICE;
 
   if (tid == 0) {
-    for (int s = 0; s < kStStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < kStStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kStCWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&pr[s], kStCWarps * V); mbar_init(&kr[s], V); }
+    for (int s = 0; s < 3; ++s) mbar_init(&rbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-
-  auto issue = [&](int tt) {   // thread 0 only
-    const int s = tt % kStStages;
-    const int64_t r0 = lo + (int64_t)tt * TN;
-    const int rows = (int)min<int64_t>(TN, hi - r0);
-    mbar_expect_tx(&full[s], (uint32_t)(rows * SLICE * 4));
-    for (int r = 0; r < rows; ++r)
-      bulk_g2s(tiles + ((size_t)s * TN + r) * SLICE, slice0 + (r0 + r) * a.D, SLICE * 4, &full[s]);
-  };
-  if (tid == 0)
-    for (int tt = 0; tt < min(ntiles, kStStages - 2); ++tt) issue(tt);
-
-  // query slice and accumulators in registers: thread owns floats [v*kStThreads*4 + tid*4, +4) of the slice
-  float4 xr[Q][VPT], acc[Q][VPT];
-#pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    const int qs = min(q, a.q_real - 1);
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-      xr[q][v] = *reinterpret_cast<const float4*>(a.x + (int64_t)qs * a.D + (int64_t)crank * SLICE +
-                                                  (v * kStThreads + tid) * 4);
-      acc[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  float zacc = 0.f;            // threads < V: sum of k for (row slot tid / Q, query tid % Q)
-  float xs_q = 0.f;
-  if (tid < V) xs_q = a.xsq[min(tid % Q, a.q_real - 1)];
-  float nsq_prev = 0.f;        // sqnorm of the row this thread finalises in phase 2 (loaded one tile ahead)
-
-  // all CTAs of the cluster must have started (their smem must exist) before the first remote store
+  // every CTA of the cluster has initialised its barriers before any remote store can target them
   cluster_arrive();
   cluster_wait();
 
-  for (int t = 0; t <= ntiles; ++t) {
-    float nsq_cur = 0.f;
-    if (t < ntiles) {
-      // ---------------- phase 1: partial dots of tile t ----------------
-      const int s = t % kStStages;
-      const int64_t r0 = lo + (int64_t)t * TN;
-      const int rows = (int)min<int64_t>(TN, hi - r0);
-      if (tid < V && tid / Q < rows) nsq_cur = a.sqnorm[r0 + tid / Q];
-      mbar_wait(&full[s], (uint32_t)((t / kStStages) & 1));
-      float part[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) part[i] = 0.f;
-      const float* tile = tiles + (size_t)s * TN * SLICE;
-#pragma unroll
-      for (int r = 0; r < TN; ++r) {
-        if (r < rows) {
-#pragma unroll
-          for (int v = 0; v < VPT; ++v) {
-            const float4 b = *reinterpret_cast<const float4*>(tile + (size_t)r * SLICE + (v * kStThreads + tid) * 4);
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              float p = part[r * Q + q];
-              p = fmaf(b.x, xr[q][v].x, p);
-              p = fmaf(b.y, xr[q][v].y, p);
-              p = fmaf(b.z, xr[q][v].z, p);
-              p = fmaf(b.w, xr[q][v].w, p);
-              part[r * Q + q] = p;
-            }
-          }
-        }
+  if (warp == kStCWarps) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      const float* slice0 = a.bank + (int64_t)crank * SLICE;
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kStStages;
+        if (t >= kStStages) mbar_wait(&empty[s], (uint32_t)(((t / kStStages) + 1) & 1));
+        const int64_t r0 = lo + (int64_t)t * TN;
+        const int rows = (int)min((int64_t)TN, hi - r0);
+        mbar_expect_tx(&full[s], (uint32_t)(rows * SLICE * 4));
+        for (int r = 0; r < rows; ++r)
+          bulk_g2s(tiles + ((size_t)s * TN + r) * SLICE, slice0 + (r0 + r) * a.D, SLICE * 4, &full[s]);
       }
-      warp_reduce_scatter<V>(part, lane);
-      if (warp_value_owner<V>(lane)) wp[warp * V + warp_value_index<V>(lane)] = part[0];
     }
-    __syncthreads();   // A_t: warp partials visible; every thread is done accumulating tile t-2
-    if (tid == 0 && t + kStStages - 2 < ntiles) issue(t + kStStages - 2);
-    if (t < ntiles && tid < V) {
-      float sum = 0.f;
+  } else if (warp == kStCWarps + 1) {
+    // =========================== weights ===========================
+    if (lane < V) {
+      const int r = lane / Q, q = lane % Q;
+      const float xs_q = a.xsq[min(q, a.q_real - 1)];
+      float zacc = 0.f;
+      for (int t = 0; t < ntiles; ++t) {
+        const int64_t r0 = lo + (int64_t)t * TN;
+        const int rows = (int)min((int64_t)TN, hi - r0);
+        const float nsq = (r < rows) ? a.sqnorm[r0 + r] : 0.f;
+        mbar_wait(&pr[t & 1], (uint32_t)((t >> 1) & 1));
+        float sum = 0.f;
+        const float* w0 = wp + (size_t)(t & 1) * kStCWarps * V + lane;
 #pragma unroll
-      for (int w = 0; w < kStWarps; ++w) sum += wp[w * V + tid];
-      float* slot = recv + ((size_t)(t % 3) * kStMaxCluster + crank) * V + tid;
-      for (uint32_t peer = 0; peer < csize; ++peer) st_remote(slot, peer, sum);
-    }
-    cluster_arrive();
-
-    if (t > 0) {
-      // ---------------- phase 2: finish tile t-1 ----------------
-      const int tp = t - 1;
-      const int s = tp % kStStages;
-      const int64_t r0 = lo + (int64_t)tp * TN;
-      const int rows = (int)min<int64_t>(TN, hi - r0);
-      if (tid < V) {
-        const int r = tid / Q, q = tid % Q;
+        for (int w = 0; w < kStCWarps; ++w) sum += w0[w * V];
+        if (lane == 0) mbar_expect_tx(&rbar[t % 3], csize * V * 4);
+        float* slot = recv + ((size_t)(t % 3) * kStMaxCluster + crank) * V + lane;
+        for (uint32_t peer = 0; peer < csize; ++peer) st_async_remote(slot, &rbar[t % 3], peer, sum);
+        mbar_wait(&rbar[t % 3], (uint32_t)((t / 3) & 1));     // every peer's partial of tile t has landed
         float k = 0.f;
         if (r < rows) {
           float dot = 0.f;
-          const float* slot = recv + (size_t)(tp % 3) * kStMaxCluster * V + tid;
-          for (uint32_t src = 0; src < csize; ++src) dot += slot[src * V];
-          const float d = dist_from_dot(xs_q, nsq_prev, dot, a.alpha, a.power);
+          const float* rs = recv + (size_t)(t % 3) * kStMaxCluster * V + lane;
+          for (uint32_t src = 0; src < csize; ++src) dot += rs[src * V];
+          const float d = dist_from_dot(xs_q, nsq, dot, a.alpha, a.power);
           k = expf(-d * a.inv2s2);
           if (crank == 0 && a.k_out && q < a.q_real) a.k_out[(int64_t)q * a.N + r0 + r] = k;
         }
-        ks[tid] = k;
+        ks[(t & 1) * V + lane] = k;
         zacc += k;
+        mbar_arrive(&kr[t & 1]);
       }
-      __syncthreads();   // B_t
-      const float* tile = tiles + (size_t)s * TN * SLICE;
+      if (crank == 0) zred[lane] = zacc;
+    }
+    __syncwarp();
+    if (crank == 0 && lane < Q && lane < a.q_real) {
+      float z = 0.f;
+      for (int r = 0; r < TN; ++r) z += zred[r * Q + lane];
+      a.part_z[(int64_t)cid * a.q_real + lane] = z;
+    }
+  } else {
+    // =========================== compute warps ===========================
+    // thread owns floats [v*kStCompute*4 + tid*4, +4) of the slice, for every query row
+    float4 xr[Q][VPT], acc[Q][VPT];
 #pragma unroll
-      for (int r = 0; r < TN; ++r) {
-        if (r < rows) {
+    for (int q = 0; q < Q; ++q) {
+      const int qs = min(q, a.q_real - 1);
 #pragma unroll
-          for (int v = 0; v < VPT; ++v) {
-            const float4 b = *reinterpret_cast<const float4*>(tile + (size_t)r * SLICE + (v * kStThreads + tid) * 4);
+      for (int v = 0; v < VPT; ++v) {
+        xr[q][v] = *reinterpret_cast<const float4*>(a.x + (int64_t)qs * a.D + (int64_t)crank * SLICE +
+                                                    (v * kStCompute + tid) * 4);
+        acc[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    for (int t = 0; t <= ntiles; ++t) {
+      if (t < ntiles) {
+        // ---------------- phase 1: partial dots of tile t ----------------
+        const int s = t % kStStages;
+        const int rows = (int)min((int64_t)TN, hi - (lo + (int64_t)t * TN));
+        mbar_wait(&full[s], (uint32_t)((t / kStStages) & 1));
+        float part[V];
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              const float k = ks[r * Q + q];
-              acc[q][v].x = fmaf(k, b.x, acc[q][v].x);
-              acc[q][v].y = fmaf(k, b.y, acc[q][v].y);
-              acc[q][v].z = fmaf(k, b.z, acc[q][v].z);
-              acc[q][v].w = fmaf(k, b.w, acc[q][v].w);
+        for (int i = 0; i < V; ++i) part[i] = 0.f;
+        const float* tile = tiles + (size_t)s * TN * SLICE;
+#pragma unroll
+        for (int r = 0; r < TN; ++r) {
+          if (r < rows) {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) {
+              const float4 b = *reinterpret_cast<const float4*>(tile + (size_t)r * SLICE + (v * kStCompute + tid) * 4);
+#pragma unroll
+              for (int q = 0; q < Q; ++q) {
+                float p = part[r * Q + q];
+                p = fmaf(b.x, xr[q][v].x, p);
+                p = fmaf(b.y, xr[q][v].y, p);
+                p = fmaf(b.z, xr[q][v].z, p);
+                p = fmaf(b.w, xr[q][v].w, p);
+                part[r * Q + q] = p;
+              }
             }
           }
         }
+        warp_reduce_scatter<V>(part, lane);
+        if (warp_value_owner<V>(lane)) {
+          wp[((size_t)(t & 1) * kStCWarps + warp) * V + warp_value_index<V>(lane)] = part[0];
+          mbar_arrive(&pr[t & 1]);
+        }
+      }
+      if (t > 0) {
+        // ---------------- phase 2: accumulate tile t-1 with its weights ----------------
+        const int tp = t - 1;
+        const int s = tp % kStStages;
+        const int rows = (int)min((int64_t)TN, hi - (lo + (int64_t)tp * TN));
+        mbar_wait(&kr[tp & 1], (uint32_t)((tp >> 1) & 1));
+        const float* tile = tiles + (size_t)s * TN * SLICE;
+        const float* kt = ks + (tp & 1) * V;
+#pragma unroll
+        for (int r = 0; r < TN; ++r) {
+          if (r < rows) {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) {
+              const float4 b = *reinterpret_cast<const float4*>(tile + (size_t)r * SLICE + (v * kStCompute + tid) * 4);
+#pragma unroll
+              for (int q = 0; q < Q; ++q) {
+                const float k = kt[r * Q + q];
+                acc[q][v].x = fmaf(k, b.x, acc[q][v].x);
+                acc[q][v].y = fmaf(k, b.y, acc[q][v].y);
+                acc[q][v].z = fmaf(k, b.z, acc[q][v].z);
+                acc[q][v].w = fmaf(k, b.w, acc[q][v].w);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
       }
     }
-    nsq_prev = nsq_cur;
-    cluster_wait();
-  }
-
-  // ---------------- write this cluster's partial sums ----------------
+    // ---------------- write this cluster's partial sums ----------------
 #pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    if (q < a.q_real) {
+    for (int q = 0; q < Q; ++q) {
+      if (q < a.q_real) {
 #pragma unroll
-      for (int v = 0; v < VPT; ++v)
-        *reinterpret_cast<float4*>(a.part_num + ((int64_t)cid * a.q_real + q) * a.D + (int64_t)crank * SLICE +
-                                   (v * kStThreads + tid) * 4) = acc[q][v];
-    }
-  }
-  if (crank == 0) {
-    __syncthreads();
-    if (tid < 64) zred[tid] = (tid < V) ? zacc : 0.f;
-    __syncthreads();
-    if (tid < Q && tid < a.q_real) {
-      float z = 0.f;
-      for (int r = 0; r < TN; ++r) z += zred[r * Q + tid];
-      a.part_z[(int64_t)cid * a.q_real + tid] = z;
+        for (int v = 0; v < VPT; ++v)
+          *reinterpret_cast<float4*>(a.part_num + ((int64_t)cid * a.q_real + q) * a.D + (int64_t)crank * SLICE +
+                                     (v * kStCompute + tid) * 4) = acc[q][v];
+      }
     }
   }
   // no CTA may exit while a peer can still write into its shared memory
+  __syncwarp();
   cluster_arrive();
   cluster_wait();
 }
 
-// num[q][d] = sum_c part[c][q][d] ; z[q] = sum_c part_z[c][q]
+// num[q][d] = sum_c part[c][q][d] ; z[q] = sum_c part_z[c][q].  Block = 32 float4 columns x 8 cluster
+// groups: every thread sums a strided subset of the per-cluster partials (independent loads), then the
+// 8 groups are combined through shared memory in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 k_stream_reduce(const float* __restrict__ part_num, const float* __restrict__ part_z, int ncl, int64_t QD,
                 int Q, float* __restrict__ num, float* __restrict__ z) {
-  const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  __shared__ float4 sh[8][32];
+  const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int64_t j = ((int64_t)blockIdx.x * 32 + col) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (j < QD) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < ncl; ++c) {
-      const float4 p = *reinterpret_cast<const float4*>(part_num + (int64_t)c * QD + j);
+#pragma unroll 4
+    for (int c = grp; c < ncl; c += 8) {
+      const float4 p = ld_stream4(part_num + (int64_t)c * QD + j);
+      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+  }
+  sh[grp][col] = s;
+  __syncthreads();
+  if (grp == 0 && j < QD) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) {
+      const float4 p = sh[g][col];
       s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
     }
     *reinterpret_cast<float4*>(num + j) = s;
   }
   if (blockIdx.x == 0 && threadIdx.x < Q) {
-    float s = 0.f;
-    for (int c = 0; c < ncl; ++c) s += part_z[(int64_t)c * Q + threadIdx.x];
-    z[threadIdx.x] = s;
+    float t = 0.f;
+    for (int c = 0; c < ncl; ++c) t += part_z[(int64_t)c * Q + threadIdx.x];
+    z[threadIdx.x] = t;
   }
 }
 
@@ -325,9 +358,11 @@ static StreamPlan plan_stream(int64_t Q, int64_t N, int64_t D) {
   if (Q < 1 || Q > 8 || N < 1) return p;
   p.qt = Q <= 1 ? 1 : (Q <= 2 ? 2 : (Q <= 4 ? 4 : 8));
   // slice = vpt * 2048 floats, cluster size = D / slice must be a power of two in [1, 8]
-  for (int vpt : {1, 2, 4}) {
+  static const int forced_vpt = [] { const char* e = getenv("SDN_STREAM_VPT"); return e ? atoi(e) : 0; }();
+  for (int vpt : {4, 2, 1}) {
+    if (forced_vpt && vpt != forced_vpt) continue;
     if (vpt > 1 && p.qt * vpt > 8) continue;
-    const int64_t slice = (int64_t)vpt * kStThreads * 4;
+    const int64_t slice = (int64_t)vpt * kStCompute * 4;
     if (D % slice) continue;
     const int64_t cs = D / slice;
     if (cs < 1 || cs > 8 || (cs & (cs - 1))) continue;
@@ -345,9 +380,12 @@ static int launch_stream_t(const StreamArgs& a, int cs, int max_clusters_hint, i
   auto kern = k_stream<Q, VPT, TN>;
   constexpr size_t smem = stream_smem_bytes<Q, VPT, TN>();
   static bool configured = false;
-  static int max_clusters = 0;
+  static int max_clusters_by_cs[kStMaxCluster + 1] = {0};
   if (!configured) {
     SDN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  if (max_clusters_by_cs[cs] == 0) {
     cudaLaunchConfig_t probe{};
     probe.gridDim = dim3(kNumSMs / cs * cs);
     probe.blockDim = dim3(kStThreads);
@@ -358,9 +396,9 @@ static int launch_stream_t(const StreamArgs& a, int cs, int max_clusters_hint, i
     probe.attrs = at; probe.numAttrs = 1;
     int n = 0;
     SDN_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &probe));
-    max_clusters = std::max(1, n);
-    configured = true;
+    max_clusters_by_cs[cs] = std::max(1, n);
   }
+  const int max_clusters = max_clusters_by_cs[cs];
   int ncl = std::min(max_clusters, max_clusters_hint);
   ncl = (int)std::min<int64_t>(ncl, std::max<int64_t>(1, cdiv(a.N, TN)));
   *ncl_out = ncl;
@@ -410,7 +448,7 @@ int stream_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D,
 #undef SDN_ST_CASE
   if (rc) return rc;
   const int64_t QD = Q * D;
-  k_stream_reduce<<<(unsigned)cdiv(QD, 1024), 256, 0, st>>>(a.part_num, a.part_z, ncl, QD, (int)Q, num, z);
+  k_stream_reduce<<<(unsigned)cdiv(QD, 128), 256, 0, st>>>(a.part_num, a.part_z, ncl, QD, (int)Q, num, z);
   SDN_LAUNCHED();
   return SDN_OK;
 }

@@ -61,6 +61,17 @@ def shard_bounds(n: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def merge_partials(packed: torch.Tensor, group) -> torch.Tensor:
+    """The one exchange step of the N-sharded projection: every rank holds the
+    un-normalised sums over its bank shard packed as [Q*D floats of num | Q floats of z]; one
+    all-reduce(SUM) leaves the full-bank sums on every rank, which then all run the same epilogue
+    (latents stay replicated, no broadcast).  ``group`` None means single GPU: nothing to do."""
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
 class _Scratch:
     __slots__ = ("num", "z", "xsq", "xq", "denom", "gate", "mean", "ws", "ws_bytes", "packed")
 
@@ -137,9 +148,7 @@ class Projector:
                                      1.0 / (2.0 * float(sigma) ** 2), int(dist_power), float(bank_alpha),
                                      None if z_only else nv.ptr(s.num), nv.ptr(s.z), nv.ptr(k_out),
                                      nv.ptr(s.ws), s.ws_bytes, self.path, st))
-        if self.group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(s.z if z_only else s.packed, op=dist.ReduceOp.SUM, group=self.group)
+        merge_partials(s.z if z_only else s.packed, self.group)
         return s
 
     # -- step 3: epilogues ---------------------------------------------------------------------

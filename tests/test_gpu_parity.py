@@ -80,6 +80,15 @@ SHAPES = [  # (name, Q, N, C, H, W)
     ("ragged", 3, 37, 4, 8, 8),
     ("one-negative", 2, 1, 4, 8, 8),
     ("q5-n100", 5, 100, 4, 16, 16),
+    # shapes the one-pass cluster kernel takes (D / 2048 a power of two <= 8, Q <= 8)
+    ("stream-q2", 2, 100, 4, 64, 64),
+    ("stream-q4", 4, 131, 4, 64, 64),
+    ("stream-q8", 8, 64, 4, 64, 64),
+    ("stream-q3-tiny-n", 3, 5, 4, 64, 64),
+    ("stream-q5-n1", 5, 1, 4, 64, 64),
+    ("stream-d8192", 2, 50, 2, 64, 64),
+    ("stream-d2048", 1, 40, 2, 32, 32),
+    ("stream-sd3-512", 2, 40, 16, 64, 64),
 ]
 
 
