@@ -1,11 +1,522 @@
-// tcgen05 / TMEM / TMA two-phase kernels for batched calls.  Filled in below the generic path.
+// tcgen05 / TMEM / TMA path for batched calls (8 < Q <= 64): the two contractions of the projection run on
+// the 5th-generation tensor cores.
+//
+// Operands are bf16 hi/lo pairs (v = hi + lo to ~2^-17): three bf16 MMAs per contraction give fp32-class
+// dot products, which the un-squared distance needs ("exactness vs tensor cores").  The bank planes
+// are made once by sdn_bank_prepare; the query planes and the weight planes are made per call.
+//
+//   k_umma_xprep    xq [Q,D] fp32 -> X planes [128][D] bf16 (rows 0..63 hi, 64..127 lo, zero padded)
+//   k_umma_dots     phase A   S^T[i][r] += sum_d X[r][d] * (hi+lo)[i][d]      A = X (K-major), B = bank rows
+//                   (K-major), accumulator [128 stacked query rows x 128 bank rows] in TMEM, split-K over D
+//   k_umma_weights  k_qi = exp(-dist/2sigma^2) from S^T, z_q, and the weight planes P [128][Npad] bf16
+//   k_umma_accum    phase B   num[q][d] = sum_i P[q][i] * (hi+lo)[i][d]      A = bank^T (MN-major, straight
+//                   from the row-major planes), B = P (K-major), accumulator [128 d x 128 stacked q] in TMEM
+//
+// Both GEMM kernels: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> global).  All smem tiles are 128B-swizzled as written by TMA.
+//
+// Replaces repellency_methods_fast.py:249-250 (cdist + the [Q,N,D+1] broadcast) for batched queries.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <mutex>
+
 #include "sdn_internal.h"
 
 namespace sdn {
-bool umma_supported(int64_t, int64_t, int64_t, const void*) { return false; }
-size_t umma_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-int umma_partial(const void*, const float*, int64_t, int64_t, const float*, const float*, int64_t, float,
-                 int, float, float*, float*, float*, void*, size_t, cudaStream_t) {
-  return SDN_E_UNSUPPORTED;
+
+constexpr int kUK = 64;          // bf16 elements per K block = one 128-byte swizzle row
+constexpr int kUStack = 128;     // stacked query rows: [0,64) hi parts, [64,128) lo parts
+constexpr int kUQ = 64;          // max query rows per launch
+constexpr int kUBankTile = 128;  // bank rows per phase-A tile (MMA N)
+constexpr int kUDBlock = 128;    // d per phase-B CTA (MMA M)
+constexpr int kUStages = 4;
+constexpr int kUThreads = 192;
+constexpr uint32_t kTileBytes = 128 * 128;   // a [128 rows][64 bf16] tile = 16 KiB
+constexpr uint32_t kStageBytes = 3 * kTileBytes;
+constexpr size_t kUSmemBytes = kUStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void u_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(u_smem(bar)), "r"(count));
 }
+__device__ __forceinline__ void u_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(u_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(u_smem(bar)), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();   // a broken pipeline must not hang the GPU
+  }
+}
+__device__ __forceinline__ void u_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(u_smem(dst)), "l"(map), "r"(u_smem(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void u_prefetch_map(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void u_tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(u_smem(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void u_tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void u_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void u_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void u_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrive when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void u_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void u_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (sm_100 format): 128-byte swizzle, version 1.
+//   K-major  tile [rows][64 bf16]: 8-row groups 1024 B apart (SBO); LBO unused (1).
+//   MN-major tile [k rows][64 bf16] x (MN blocks `lbo_bytes` apart): 8-row k groups 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t u_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.
+__host__ __device__ constexpr uint32_t u_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct USmem {
+  uint8_t* tiles;       // [stages][3][16 KiB], 1024-byte aligned
+  uint64_t* full;       // [stages]
+  uint64_t* empty;      // [stages]
+  uint64_t* acc_full;   // [2]
+  uint64_t* acc_empty;  // [2]
+  uint32_t* tmem_base;  // [1]
+};
+__device__ __forceinline__ USmem u_carve(unsigned char* raw) {
+  USmem s;
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023;
+  s.tiles = reinterpret_cast<uint8_t*>(a);
+  s.full = reinterpret_cast<uint64_t*>(s.tiles + (size_t)kUStages * kStageBytes);
+  s.empty = s.full + kUStages;
+  s.acc_full = s.empty + kUStages;
+  s.acc_empty = s.acc_full + 2;
+  s.tmem_base = reinterpret_cast<uint32_t*>(s.acc_empty + 2);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------ query planes
+__global__ void __launch_bounds__(256)
+k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes) {
+  const int q = blockIdx.y;   // 0..63
+  const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (j >= D) return;
+  __nv_bfloat16 h[4], l[4];
+  if (q < Q) {
+    const float4 v = *reinterpret_cast<const float4*>(xq + (int64_t)q * D + j);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      h[u] = __float2bfloat16_rn(f[u]);
+      l[u] = __float2bfloat16_rn(f[u] - __bfloat162float(h[u]));
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h[u] = l[u] = __float2bfloat16_rn(0.f);
+  }
+  *reinterpret_cast<uint2*>(planes + (int64_t)q * D + j) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(planes + (int64_t)(kUQ + q) * D + j) = *reinterpret_cast<const uint2*>(l);
+}
+
+// ------------------------------------------------------------------------------------------ phase A
+// grid (row tiles, k splits).  S_T [Npad][128] fp32: S_T[i][r] = sum over this split of X[r][d] * bank[i][d].
+//
+// The tensor core adds into its fp32 accumulator with truncation, and near a negative the distance is the
+// small difference of large dot products, so long accumulation chains cost accuracy (measured: 43 K-blocks in
+// one chain -> 3.6e-4 on the weights).  The MMA warp therefore alternates between two TMEM accumulators every
+// kUChunk K-blocks and the epilogue warps drain the finished one into fp32 registers (round-to-nearest adds).
+constexpr int kUChunk = 4;
+
+__global__ void __launch_bounds__(kUThreads, 1)
+k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
+            const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int kblocks_total, int ksplit,
+            int use_atomic) {
+  extern __shared__ unsigned char smem_raw[];
+  const USmem sm = u_carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kUBankTile;
+  const int kb0 = (int)((int64_t)blockIdx.y * kblocks_total / ksplit);
+  const int kb1 = (int)((int64_t)(blockIdx.y + 1) * kblocks_total / ksplit);
+  const int nkb = kb1 - kb0;
+  const int nchunks = (nkb + kUChunk - 1) / kUChunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kUStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kUBankTile);
+  u_fence_before();
+  __syncthreads();
+  u_fence_after();
+  const uint32_t tmem = *sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kUStages;
+        if (i >= kUStages) u_mbar_wait(&sm.empty[s], (uint32_t)(((i / kUStages) + 1) & 1));
+        uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
+        u_mbar_expect_tx(&sm.full[s], kStageBytes);
+        const int kc = (kb0 + i) * kUK;
+        u_tma_2d(st, &tm_x, kc, 0, &sm.full[s]);
+        u_tma_2d(st + kTileBytes, &tm_hi, kc, row0, &sm.full[s]);
+        u_tma_2d(st + 2 * kTileBytes, &tm_lo, kc, row0, &sm.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = u_idesc(kUStack, kUBankTile, 0, 0);
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c >= 2) {
+          u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((c >> 1) + 1) & 1));
+          u_fence_after();
+        }
+        const uint32_t acc = tmem + (uint32_t)(buf * kUBankTile);
+        const int i1 = min(nkb, (c + 1) * kUChunk);
+        for (int i = c * kUChunk; i < i1; ++i) {
+          const int s = i % kUStages;
+          u_mbar_wait(&sm.full[s], (uint32_t)((i / kUStages) & 1));
+          u_fence_after();
+          const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < kUK / 16; ++kk) {
+            const uint64_t a = u_desc(base + kk * 32, 16, 1024);
+            const uint64_t bh = u_desc(base + kTileBytes + kk * 32, 16, 1024);
+            const uint64_t bl = u_desc(base + 2 * kTileBytes + kk * 32, 16, 1024);
+            u_mma(acc, a, bh, idesc, (i > c * kUChunk || kk > 0) ? 1u : 0u);
+            u_mma(acc, a, bl, idesc, 1u);
+          }
+          u_commit(&sm.empty[s]);
+        }
+        u_commit(&sm.acc_full[buf]);
+      }
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); lane index = stacked query row
+    const int lq = warp & 3;
+    float sum[kUBankTile];
+#pragma unroll
+    for (int j = 0; j < kUBankTile; ++j) sum[j] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      u_mbar_wait(&sm.acc_full[buf], (uint32_t)((c >> 1) & 1));
+      u_fence_after();
+      const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kUBankTile);
+#pragma unroll
+      for (int cc = 0; cc < kUBankTile / 32; ++cc) {
+        float v[32];
+        u_tmem_ld32(tl + (uint32_t)(cc * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[cc * 32 + j] += v[j];
+      }
+      u_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
+    }
+    const int r = lq * 32 + lane;
+    float* dst = S_T + (int64_t)row0 * kUStack + r;
+    if (use_atomic) {
+#pragma unroll
+      for (int j = 0; j < kUBankTile; ++j) atomicAdd(dst + (int64_t)j * kUStack, sum[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kUBankTile; ++j) dst[(int64_t)j * kUStack] = sum[j];
+    }
+  }
+  u_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    u_fence_after();
+    u_tmem_dealloc(tmem, 2 * kUBankTile);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ weights
+// block = 128 threads, 32 bank rows x 64 query rows.
+__global__ void __launch_bounds__(128)
+k_umma_weights(const float* __restrict__ S_T, const float* __restrict__ sqnorm, const float* __restrict__ xsq,
+               int N, int64_t Npad, int Q, float inv2s2, int power, float alpha,
+               __nv_bfloat16* __restrict__ P, float* __restrict__ z, float* __restrict__ k_out) {
+  __shared__ float kq[kUQ][33];
+  const int r0 = blockIdx.x * 32;
+  for (int idx = threadIdx.x; idx < 32 * kUQ; idx += 128) {
+    const int row = idx / kUQ, q = idx % kUQ;
+    const int i = r0 + row;
+    float k = 0.f;
+    if (i < N && q < Q) {
+      const float* s = S_T + (int64_t)i * kUStack;
+      const float dot = s[q] + s[kUQ + q];
+      k = expf(-dist_from_dot(xsq[q], sqnorm[i], dot, alpha, power) * inv2s2);
+    }
+    kq[q][row] = k;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * kUQ; idx += 128) {
+    const int q = idx / 32, row = idx % 32;   // q is warp-uniform
+    const int i = r0 + row;
+    const float k = kq[q][row];
+    const __nv_bfloat16 h = __float2bfloat16_rn(k);
+    const __nv_bfloat16 l = __float2bfloat16_rn(k - __bfloat162float(h));
+    P[(int64_t)q * Npad + i] = h;
+    P[(int64_t)(kUQ + q) * Npad + i] = l;
+    if (k_out && i < N && q < Q) k_out[(int64_t)q * N + i] = k;
+    const float s = warp_sum(k);
+    if (row == 0 && q < Q && s != 0.f) atomicAdd(z + q, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ phase B
+// grid (D / 128, n splits).  num[q][d] (+)= sum_i P[q][i] * (hi+lo)[i][d] over this split's bank rows.
+__global__ void __launch_bounds__(kUThreads, 1)
+k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
+             const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
+             int rblocks_total, int nsplit, int use_atomic) {
+  extern __shared__ unsigned char smem_raw[];
+  const USmem sm = u_carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d0 = blockIdx.x * kUDBlock;
+  const int rb0 = (int)((int64_t)blockIdx.y * rblocks_total / nsplit);
+  const int rb1 = (int)((int64_t)(blockIdx.y + 1) * rblocks_total / nsplit);
+  const int nrb = rb1 - rb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kUStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
+    u_mbar_init(&sm.acc_full[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) u_tmem_alloc(sm.tmem_base, kUStack);
+  u_fence_before();
+  __syncthreads();
+  u_fence_after();
+  const uint32_t tmem = *sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
+      for (int i = 0; i < nrb; ++i) {
+        const int s = i % kUStages;
+        if (i >= kUStages) u_mbar_wait(&sm.empty[s], (uint32_t)(((i / kUStages) + 1) & 1));
+        uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
+        u_mbar_expect_tx(&sm.full[s], kStageBytes);
+        const int rc = (rb0 + i) * kUK;                   // first bank row of this block
+        u_tma_2d(st, &tm_p, rc, 0, &sm.full[s]);          // P tile [128 stacked q][64 rows]
+        // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart
+        u_tma_2d(st + kTileBytes, &tm_hi, d0, rc, &sm.full[s]);
+        u_tma_2d(st + kTileBytes + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
+        u_tma_2d(st + 2 * kTileBytes, &tm_lo, d0, rc, &sm.full[s]);
+        u_tma_2d(st + 2 * kTileBytes + 8192, &tm_lo, d0 + 64, rc, &sm.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_full = u_idesc(kUDBlock, kUStack, 1, 0);   // hi * [P_hi | P_lo]
+      constexpr uint32_t id_half = u_idesc(kUDBlock, kUQ, 1, 0);       // lo * P_hi
+      for (int i = 0; i < nrb; ++i) {
+        const int s = i % kUStages;
+        u_mbar_wait(&sm.full[s], (uint32_t)((i / kUStages) & 1));
+        u_fence_after();
+        const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < kUK / 16; ++kk) {
+          const uint64_t b = u_desc(base + kk * 32, 16, 1024);                        // P, K-major
+          const uint64_t ah = u_desc(base + kTileBytes + kk * 2048, 8192, 1024);      // bank^T, MN-major
+          const uint64_t al = u_desc(base + 2 * kTileBytes + kk * 2048, 8192, 1024);
+          u_mma(tmem, ah, b, id_full, (i > 0 || kk > 0) ? 1u : 0u);
+          u_mma(tmem, al, b, id_half, 1u);
+        }
+        u_commit(&sm.empty[s]);
+      }
+      u_commit(&sm.acc_full[0]);
+    }
+  } else {
+    // epilogue: TMEM lane = d within the block, column = stacked query row
+    const int lq = warp & 3;
+    u_mbar_wait(&sm.acc_full[0], 0);
+    u_fence_after();
+    const int64_t d = (int64_t)d0 + lq * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < kUQ / 32; ++c) {
+      float a[32], b[32];
+      u_tmem_ld32(tl + (uint32_t)(c * 32), a);            // hi*P_hi + lo*P_hi, queries [32c, 32c+32)
+      u_tmem_ld32(tl + (uint32_t)(kUQ + c * 32), b);      // hi*P_lo
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int q = c * 32 + j;
+        if (q < Q) {
+          float* o = num + (int64_t)q * D + d;
+          if (use_atomic) atomicAdd(o, a[j] + b[j]); else *o = a[j] + b[j];
+        }
+      }
+    }
+  }
+  u_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    u_fence_after();
+    u_tmem_dealloc(tmem, kUStack);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+namespace {
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_encode_once;
+
+bool load_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  return g_encode != nullptr;
+}
+
+// 2-D bf16 row-major tensor [rows][cols], box [box_rows][box_cols], 128-byte swizzle.
+int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SDN_OK : SDN_E_PARAM;
+}
+
+struct UmmaLayout {
+  int64_t npad;        // bank rows padded to 128
+  size_t off_x, off_s, off_p, total;
+};
+UmmaLayout umma_layout(int64_t N, int64_t D) {
+  UmmaLayout L;
+  L.npad = cdiv(N, 128) * 128;
+  size_t o = 0;
+  L.off_x = o; o += (size_t)kUStack * D * 2;                 // X planes
+  o = (o + 255) / 256 * 256;
+  L.off_s = o; o += (size_t)L.npad * kUStack * 4;            // S^T
+  o = (o + 255) / 256 * 256;
+  L.off_p = o; o += (size_t)kUStack * L.npad * 2;            // P planes
+  L.total = (o + 255) / 256 * 256;
+  return L;
+}
+}  // namespace
+
+bool umma_supported(int64_t Q, int64_t N, int64_t D, const void* planes) {
+  return planes != nullptr && Q >= 1 && Q <= kUQ && N >= 1 && D >= kUDBlock && D % kUDBlock == 0 &&
+         N < (1ll << 31) && D < (1ll << 31);
+}
+
+size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D) {
+  if (Q < 1 || Q > kUQ || D % kUDBlock) return 0;
+  return umma_layout(N, D).total;
+}
+
+int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                 const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
+                 float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
+  const UmmaLayout L = umma_layout(N, D);
+  if (!ws || ws_bytes < L.total) return SDN_E_WORKSPACE;
+  if (!load_encode()) return SDN_E_DEVICE;
+  static bool configured = false;
+  if (!configured) {
+    SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+    SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+    configured = true;
+  }
+  char* w = static_cast<char*>(ws);
+  __nv_bfloat16* xpl = reinterpret_cast<__nv_bfloat16*>(w + L.off_x);
+  float* S_T = reinterpret_cast<float*>(w + L.off_s);
+  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(w + L.off_p);
+  const __nv_bfloat16* hi = static_cast<const __nv_bfloat16*>(planes);
+  const __nv_bfloat16* lo = hi + N * D;
+
+  CUtensorMap tm_x, tm_hiA, tm_loA, tm_p, tm_hiB, tm_loB;
+  int rc;
+  if ((rc = make_map(&tm_x, xpl, kUStack, D, kUStack, kUK))) return rc;
+  if ((rc = make_map(&tm_hiA, hi, N, D, kUBankTile, kUK))) return rc;
+  if ((rc = make_map(&tm_loA, lo, N, D, kUBankTile, kUK))) return rc;
+  if ((rc = make_map(&tm_p, P, kUStack, L.npad, kUStack, kUK))) return rc;
+  if ((rc = make_map(&tm_hiB, hi, N, D, kUK, 64))) return rc;
+  if ((rc = make_map(&tm_loB, lo, N, D, kUK, 64))) return rc;
+
+  // query planes
+  k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xq, (int)Q, D, xpl);
+  SDN_LAUNCHED();
+
+  // phase A: split K (= D) so that roughly every SM gets one task
+  const int row_tiles = (int)(L.npad / kUBankTile);
+  const int kblocks = (int)(D / kUK);
+  int ksplit = std::max(1, std::min(kblocks / 4, (kNumSMs + row_tiles / 2) / row_tiles));
+  ksplit = std::min(ksplit, 32);
+  if (ksplit > 1) SDN_CUDA_OK(cudaMemsetAsync(S_T, 0, (size_t)L.npad * kUStack * 4, st));
+  k_umma_dots<<<dim3(row_tiles, ksplit), kUThreads, kUSmemBytes, st>>>(tm_x, tm_hiA, tm_loA, S_T, kblocks, ksplit,
+                                                                      ksplit > 1 ? 1 : 0);
+  SDN_LAUNCHED();
+
+  // weights
+  SDN_CUDA_OK(cudaMemsetAsync(z, 0, sizeof(float) * Q, st));
+  k_umma_weights<<<(unsigned)(L.npad / 32), 128, 0, st>>>(S_T, sqnorm, xsq, (int)N, L.npad, (int)Q, inv2s2, power,
+                                                         alpha, P, z, k_out);
+  SDN_LAUNCHED();
+
+  // phase B: one CTA per 128 d, bank rows split when that leaves SMs idle
+  const int dblocks = (int)(D / kUDBlock);
+  const int rblocks = (int)(L.npad / kUK);
+  int nsplit = std::max(1, std::min(rblocks / 8, kNumSMs / dblocks));
+  if (nsplit > 1) SDN_CUDA_OK(cudaMemsetAsync(num, 0, sizeof(float) * Q * D, st));
+  k_umma_accum<<<dim3(dblocks, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
+                                                                     nsplit, nsplit > 1 ? 1 : 0);
+  SDN_LAUNCHED();
+  return SDN_OK;
+}
+
 }  // namespace sdn

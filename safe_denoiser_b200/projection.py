@@ -48,6 +48,14 @@ class NegativeBank:
     def device(self):
         return self.tensor.device
 
+    def ensure_planes(self):
+        """bf16 hi/lo planes for the tcgen05 path, made on first batched use."""
+        if self.planes is None:
+            self.planes = torch.empty(2, self.N, self.D, dtype=torch.bfloat16, device=self.device)
+            nv.check(nv.lib().sdn_bank_prepare(nv.ptr(self.flat), self.N, self.D, nv.ptr(self.sqnorm),
+                                               nv.ptr(self.planes), nv.current_stream()))
+        return self.planes
+
     def shard(self, rank: int, world: int) -> "NegativeBank":
         """Contiguous N-shard [lo, hi) of this bank."""
         lo, hi = shard_bounds(self.N, rank, world)
@@ -128,6 +136,8 @@ class Projector:
         L = nv.lib()
         st = nv.current_stream()
         Q, xf = self._flat_query(x0)
+        if Q > 8 and not z_only and self.path in (nv.PATH_AUTO, nv.PATH_UMMA) and self.bank.D % 128 == 0:
+            self.bank.ensure_planes()        # batched calls go to the tcgen05 kernels
         s = self._get(Q, normalize_channels > 0)
         mo = None
         if model_out is not None:
