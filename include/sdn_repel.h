@@ -66,6 +66,12 @@ const char* sdn_error_string(int code);
 /* Number of kernels this library has launched since load (all entry points); bench.py reports it. */
 uint64_t sdn_launch_count(void);
 
+/* Per-kernel timing of the LAST sdn_repel_partial call (CUDA events on its stream).  Off by default.
+ * sdn_profile_read(i, ...) returns 1 and fills the i-th kernel's name and duration in ms (it synchronises on
+ * that kernel's end event), 0 when i is out of range.  bench.py uses it for the roofline of the dominant kernel. */
+void sdn_profile_enable(int32_t on);
+int32_t sdn_profile_read(int32_t index, char* name_out, int32_t name_cap, float* ms_out);
+
 /* ---- bank -------------------------------------------------------------------------------
  * Derived data of the proj_ref tensor, computed once at load (fast.py:109-111 loads the tensor;
  * torch.cdist recomputes ||n_i||^2 on every call, fast.py:249).

@@ -21,6 +21,8 @@ SIGNATURES = {
     "sdn_abi_version": (C.c_int, []),
     "sdn_error_string": (C.c_char_p, [C.c_int]),
     "sdn_launch_count": (C.c_uint64, []),
+    "sdn_profile_enable": (None, [_i32]),
+    "sdn_profile_read": (_i32, [_i32, C.c_char_p, _i32, C.POINTER(C.c_float)]),
     "sdn_bank_prepare": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "sdn_query_prepare": (C.c_int, [_p, _p, _f, _f, _i64, _i64, _i32, _p, _p, _p, _p]),
     "sdn_repel_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
@@ -83,6 +85,21 @@ def ptr(t):
 def current_stream():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def profile_enable(on=True):
+    lib().sdn_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """[(kernel name, ms)] of the last sdn_repel_partial call (needs profile_enable(True) before it)."""
+    out, i = [], 0
+    buf = C.create_string_buffer(64)
+    ms = C.c_float(0.0)
+    while lib().sdn_profile_read(i, buf, 64, C.byref(ms)):
+        out.append((buf.value.decode(), float(ms.value)))
+        i += 1
+    return out
 
 
 def launch_count():

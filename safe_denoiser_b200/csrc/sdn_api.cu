@@ -7,6 +7,7 @@
 
 namespace sdn {
 std::atomic<uint64_t> g_launches{0};
+Prof g_prof;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -46,6 +47,22 @@ const char* sdn_error_string(int code) {
   return "unknown error";
 }
 
+void sdn_profile_enable(int32_t on) { g_prof.enabled = on != 0; g_prof.reset(); }
+
+int32_t sdn_profile_read(int32_t index, char* name_out, int32_t name_cap, float* ms_out) {
+  if (index < 0 || index >= g_prof.n) return 0;
+  const ProfSlot& s = g_prof.slot[index];
+  if (cudaEventSynchronize(s.e1) != cudaSuccess) return 0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, s.e0, s.e1) != cudaSuccess) return 0;
+  if (ms_out) *ms_out = ms;
+  if (name_out && name_cap > 0) {
+    strncpy(name_out, s.name, (size_t)name_cap - 1);
+    name_out[name_cap - 1] = 0;
+  }
+  return 1;
+}
+
 size_t sdn_repel_workspace_bytes(int64_t Q, int64_t N, int64_t D, int32_t path) {
   if (Q <= 0 || N <= 0 || D <= 0) return 0;
   size_t need = generic_workspace_bytes(Q, N);
@@ -65,6 +82,7 @@ int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes
   if (D % 4 != 0 || (bank && !aligned16(bank)) || !aligned16(xq) || (num_out && !aligned16(num_out)))
     return SDN_E_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
+  g_prof.reset();
   const int chosen = num_out ? pick_path(path, Q, N, D, planes) : SDN_PATH_GENERIC;
   switch (chosen) {
     case SDN_PATH_STREAM:
@@ -85,12 +103,19 @@ int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes
     if (!workspace || workspace_bytes < generic_workspace_bytes(Q, N)) return SDN_E_WORKSPACE;
     S = static_cast<float*>(workspace);
   }
+  int pid = g_prof.begin("k_dots", st);
   int rc = generic_dots(bank, N, D, xq, Q, S, st);
+  g_prof.end(pid, st);
   if (rc) return rc;
+  pid = g_prof.begin("k_weights", st);
   rc = generic_weights(S, sqnorm, xsq, Q, N, inv_two_sigma_sq, dist_power, bank_alpha, z_out, st);
+  g_prof.end(pid, st);
   if (rc) return rc;
   if (!num_out) return SDN_OK;
-  return generic_accum(bank, N, D, S, Q, num_out, st);
+  pid = g_prof.begin("k_accum", st);
+  rc = generic_accum(bank, N, D, S, Q, num_out, st);
+  g_prof.end(pid, st);
+  return rc;
 }
 
 int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t D, float* x0_inout,

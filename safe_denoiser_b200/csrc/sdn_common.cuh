@@ -25,6 +25,25 @@ extern std::atomic<uint64_t> g_launches;
     if (_e != cudaSuccess) return static_cast<int>(_e);     \
   } while (0)
 
+// Optional per-kernel CUDA-event timing of the last sdn_repel_partial call (sdn_profile_enable).
+struct ProfSlot { const char* name; cudaEvent_t e0, e1; };
+struct Prof {
+  bool enabled = false;
+  int n = 0;
+  ProfSlot slot[16] = {};
+  void reset() { n = 0; }
+  int begin(const char* name, cudaStream_t st) {
+    if (!enabled || n >= 16) return -1;
+    ProfSlot& s = slot[n];
+    if (!s.e0) { cudaEventCreate(&s.e0); cudaEventCreate(&s.e1); }
+    s.name = name;
+    cudaEventRecord(s.e0, st);
+    return n++;
+  }
+  void end(int id, cudaStream_t st) { if (id >= 0) cudaEventRecord(slot[id].e1, st); }
+};
+extern Prof g_prof;
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

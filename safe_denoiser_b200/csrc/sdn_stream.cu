@@ -440,15 +440,19 @@ int stream_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D,
   a.part_num = static_cast<float*>(ws);
   a.part_z = a.part_num + (size_t)hint * Q * D;
   int ncl = 0, rc = SDN_E_UNSUPPORTED;
+  int pid = g_prof.begin("k_stream", st);
 #define SDN_ST_CASE(QQ, VV, TT) \
   if (p.qt == QQ && p.vpt == VV && p.tn == TT) rc = launch_stream_t<QQ, VV, TT>(a, p.cs, hint, &ncl, st);
   SDN_ST_CASE(1, 1, 4) SDN_ST_CASE(2, 1, 4) SDN_ST_CASE(4, 1, 4) SDN_ST_CASE(8, 1, 2)
   SDN_ST_CASE(1, 2, 2) SDN_ST_CASE(2, 2, 2) SDN_ST_CASE(4, 2, 2)
   SDN_ST_CASE(1, 4, 1) SDN_ST_CASE(2, 4, 1)
 #undef SDN_ST_CASE
+  g_prof.end(pid, st);
   if (rc) return rc;
   const int64_t QD = Q * D;
+  pid = g_prof.begin("k_stream_reduce", st);
   k_stream_reduce<<<(unsigned)cdiv(QD, 128), 256, 0, st>>>(a.part_num, a.part_z, ncl, QD, (int)Q, num, z);
+  g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;
 }

@@ -8,9 +8,9 @@
 //   k_umma_xprep    xq [Q,D] fp32 -> X planes [128][D] bf16 (rows 0..63 hi, 64..127 lo, zero padded)
 //   k_umma_dots     phase A   S^T[i][r] += sum_d X[r][d] * (hi+lo)[i][d]      A = X (K-major), B = bank rows
 //                   (K-major), accumulator [128 stacked query rows x 128 bank rows] in TMEM, split-K over D
-//   k_umma_weights  k_qi = exp(-dist/2sigma^2) from S^T, z_q, and the weight planes P [128][Npad] bf16
+//   k_umma_weights  k_qi = exp(-dist/2sigma^2) from S^T, z_q, and the weight planes P [Npad][128] bf16
 //   k_umma_accum    phase B   num[q][d] = sum_i P[q][i] * (hi+lo)[i][d]      A = bank^T (MN-major, straight
-//                   from the row-major planes), B = P (K-major), accumulator [128 d x 128 stacked q] in TMEM
+//                   from the row-major planes), B = P (MN-major), accumulator [128 d x 128 stacked q] in TMEM
 //
 // Both GEMM kernels: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> global).  All smem tiles are 128B-swizzled as written by TMA.
@@ -161,7 +161,7 @@ k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------------ phase A
-// grid (row tiles, k splits).  S_T [Npad][128] fp32: S_T[i][r] = sum over this split of X[r][d] * bank[i][d].
+// grid (row tiles, k splits).  S_T [ksplit][Npad][128] fp32: S_T[s][i][r] = sum over split s of X[r][d] * bank[i][d].
 //
 // The tensor core adds into its fp32 accumulator with truncation, and near a negative the distance is the
 // small difference of large dot products, so long accumulation chains cost accuracy (measured: 43 K-blocks in
@@ -171,8 +171,8 @@ constexpr int kUChunk = 4;
 
 __global__ void __launch_bounds__(kUThreads, 1)
 k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
-            const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int kblocks_total, int ksplit,
-            int use_atomic) {
+            const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int64_t split_stride,
+            int kblocks_total, int ksplit) {
   extern __shared__ unsigned char smem_raw[];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,15 +258,11 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
     }
+    // every K split owns its own partial buffer: plain coalesced stores, summed by k_umma_weights
     const int r = lq * 32 + lane;
-    float* dst = S_T + (int64_t)row0 * kUStack + r;
-    if (use_atomic) {
+    float* dst = S_T + (int64_t)blockIdx.y * split_stride + (int64_t)row0 * kUStack + r;
 #pragma unroll
-      for (int j = 0; j < kUBankTile; ++j) atomicAdd(dst + (int64_t)j * kUStack, sum[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < kUBankTile; ++j) dst[(int64_t)j * kUStack] = sum[j];
-    }
+    for (int j = 0; j < kUBankTile; ++j) dst[(int64_t)j * kUStack] = sum[j];
   }
   u_fence_before();
   __syncthreads();
@@ -277,37 +273,54 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------ weights
-// block = 128 threads, 32 bank rows x 64 query rows.
-__global__ void __launch_bounds__(128)
-k_umma_weights(const float* __restrict__ S_T, const float* __restrict__ sqnorm, const float* __restrict__ xsq,
-               int N, int64_t Npad, int Q, float inv2s2, int power, float alpha,
-               __nv_bfloat16* __restrict__ P, float* __restrict__ z, float* __restrict__ k_out) {
-  __shared__ float kq[kUQ][33];
-  const int r0 = blockIdx.x * 32;
-  for (int idx = threadIdx.x; idx < 32 * kUQ; idx += 128) {
-    const int row = idx / kUQ, q = idx % kUQ;
-    const int i = r0 + row;
-    float k = 0.f;
-    if (i < N && q < Q) {
-      const float* s = S_T + (int64_t)i * kUStack;
-      const float dot = s[q] + s[kUQ + q];
-      k = expf(-dist_from_dot(xsq[q], sqnorm[i], dot, alpha, power) * inv2s2);
-    }
-    kq[q][row] = k;
+// One thread per (bank row, query row): sum the K-split partials, k = exp(-dist / 2 sigma^2), write the weight
+// planes P [Npad][128] bf16 (stacked query index contiguous: hi parts in columns [0,64), lo parts in [64,128)),
+// which phase B reads as an MN-major B operand.  Everything is coalesced; block = 4 bank rows x 64 query rows.
+constexpr int kWRows = 4;
+
+__global__ void __launch_bounds__(kWRows * kUQ)
+k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, const float* __restrict__ sqnorm,
+               const float* __restrict__ xsq, int N, int Q, float inv2s2, int power, float alpha,
+               __nv_bfloat16* __restrict__ P, float* __restrict__ zpart, float* __restrict__ k_out) {
+  __shared__ float zs[kWRows][kUQ];
+  const int q = threadIdx.x & (kUQ - 1);
+  const int rsub = threadIdx.x >> 6;
+  const int i = blockIdx.x * kWRows + rsub;
+  const float* s = S_T + (int64_t)i * kUStack;
+  float dot = 0.f;
+#pragma unroll 4
+  for (int sp = 0; sp < ksplit; ++sp) {
+    const float* p = s + (int64_t)sp * split_stride;
+    dot += p[q] + p[kUQ + q];
   }
+  float k = 0.f;
+  if (i < N && q < Q) k = expf(-dist_from_dot(xsq[q], sqnorm[i], dot, alpha, power) * inv2s2);
+  const __nv_bfloat16 h = __float2bfloat16_rn(k);
+  const __nv_bfloat16 l = __float2bfloat16_rn(k - __bfloat162float(h));
+  P[(int64_t)i * kUStack + q] = h;
+  P[(int64_t)i * kUStack + kUQ + q] = l;
+  if (k_out && i < N && q < Q) k_out[(int64_t)q * N + i] = k;
+  // z: per-block partials; k_umma_zreduce sums them in a fixed order (deterministic, no same-address atomics,
+  // and no serial tail: a "last block reduces" variant spent 16 us in one SM)
+  zs[rsub][q] = k;
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 32 * kUQ; idx += 128) {
-    const int q = idx / 32, row = idx % 32;   // q is warp-uniform
-    const int i = r0 + row;
-    const float k = kq[q][row];
-    const __nv_bfloat16 h = __float2bfloat16_rn(k);
-    const __nv_bfloat16 l = __float2bfloat16_rn(k - __bfloat162float(h));
-    P[(int64_t)q * Npad + i] = h;
-    P[(int64_t)(kUQ + q) * Npad + i] = l;
-    if (k_out && i < N && q < Q) k_out[(int64_t)q * N + i] = k;
-    const float s = warp_sum(k);
-    if (row == 0 && q < Q && s != 0.f) atomicAdd(z + q, s);
+  if (threadIdx.x < kUQ) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < kWRows; ++r) t += zs[r][threadIdx.x];
+    zpart[(int64_t)blockIdx.x * kUQ + threadIdx.x] = t;
   }
+}
+
+// z[q] = sum_b zpart[b][q]; one block per query row.
+__global__ void __launch_bounds__(256)
+k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__ z) {
+  __shared__ float red[33];
+  const int q = blockIdx.x;
+  float t = 0.f;
+  for (int b = threadIdx.x; b < nblocks; b += 256) t += zpart[(int64_t)b * kUQ + q];
+  t = block_sum(t, red);
+  if (threadIdx.x == 0) z[q] = t;
 }
 
 // ------------------------------------------------------------------------------------------ phase B
@@ -344,7 +357,9 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
         u_mbar_expect_tx(&sm.full[s], kStageBytes);
         const int rc = (rb0 + i) * kUK;                   // first bank row of this block
-        u_tma_2d(st, &tm_p, rc, 0, &sm.full[s]);          // P tile [128 stacked q][64 rows]
+        // P tile: two boxes of [64 rows][64 stacked q] (hi parts, lo parts), 8 KiB apart
+        u_tma_2d(st, &tm_p, 0, rc, &sm.full[s]);
+        u_tma_2d(st + 8192, &tm_p, 64, rc, &sm.full[s]);
         // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart
         u_tma_2d(st + kTileBytes, &tm_hi, d0, rc, &sm.full[s]);
         u_tma_2d(st + kTileBytes + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
@@ -354,8 +369,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t id_full = u_idesc(kUDBlock, kUStack, 1, 0);   // hi * [P_hi | P_lo]
-      constexpr uint32_t id_half = u_idesc(kUDBlock, kUQ, 1, 0);       // lo * P_hi
+      constexpr uint32_t id_full = u_idesc(kUDBlock, kUStack, 1, 1);   // hi * [P_hi | P_lo]
+      constexpr uint32_t id_half = u_idesc(kUDBlock, kUQ, 1, 1);       // lo * P_hi
       for (int i = 0; i < nrb; ++i) {
         const int s = i % kUStages;
         u_mbar_wait(&sm.full[s], (uint32_t)((i / kUStages) & 1));
@@ -363,7 +378,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
 #pragma unroll
         for (int kk = 0; kk < kUK / 16; ++kk) {
-          const uint64_t b = u_desc(base + kk * 32, 16, 1024);                        // P, K-major
+          const uint64_t b = u_desc(base + kk * 2048, 8192, 1024);                    // P^T, MN-major
           const uint64_t ah = u_desc(base + kTileBytes + kk * 2048, 8192, 1024);      // bank^T, MN-major
           const uint64_t al = u_desc(base + 2 * kTileBytes + kk * 2048, 8192, 1024);
           u_mma(tmem, ah, b, id_full, (i > 0 || kk > 0) ? 1u : 0u);
@@ -431,38 +446,67 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
   return r == CUDA_SUCCESS ? SDN_OK : SDN_E_PARAM;
 }
 
+int umma_ksplit(int64_t npad, int64_t D) {
+  const int row_tiles = (int)(npad / kUBankTile);
+  const int kblocks = (int)(D / kUK);
+  int ksplit = std::max(1, std::min(kblocks / 4, (kNumSMs + row_tiles / 2) / row_tiles));
+  return std::min(ksplit, 16);
+}
+
 struct UmmaLayout {
   int64_t npad;        // bank rows padded to 128
-  size_t off_x, off_s, off_p, total;
+  int ksplit;
+  size_t off_x, off_s, off_p, off_z, total;
 };
 UmmaLayout umma_layout(int64_t N, int64_t D) {
   UmmaLayout L;
   L.npad = cdiv(N, 128) * 128;
+  L.ksplit = umma_ksplit(L.npad, D);
   size_t o = 0;
   L.off_x = o; o += (size_t)kUStack * D * 2;                 // X planes
   o = (o + 255) / 256 * 256;
-  L.off_s = o; o += (size_t)L.npad * kUStack * 4;            // S^T
+  L.off_s = o; o += (size_t)L.ksplit * L.npad * kUStack * 4; // S^T, one partial per K split
   o = (o + 255) / 256 * 256;
   L.off_p = o; o += (size_t)kUStack * L.npad * 2;            // P planes
+  o = (o + 255) / 256 * 256;
+  L.off_z = o; o += (size_t)(L.npad / kWRows) * kUQ * 4 + 256;   // per-block z partials + completion counter
   L.total = (o + 255) / 256 * 256;
   return L;
 }
 }  // namespace
 
 bool umma_supported(int64_t Q, int64_t N, int64_t D, const void* planes) {
-  return planes != nullptr && Q >= 1 && Q <= kUQ && N >= 1 && D >= kUDBlock && D % kUDBlock == 0 &&
+  return planes != nullptr && Q >= 1 && N >= 1 && D >= kUDBlock && D % kUDBlock == 0 &&
          N < (1ll << 31) && D < (1ll << 31);
 }
 
 size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D) {
-  if (Q < 1 || Q > kUQ || D % kUDBlock) return 0;
+  if (Q < 1 || D % kUDBlock) return 0;
   return umma_layout(N, D).total;
 }
 
+static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                           const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
+                           float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// More than 64 query rows: one two-phase pass over the bank per group of 64 (the TMEM accumulator of phase B
+// holds 128 d x 128 stacked query columns).
 int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                  const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
                  float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
+  for (int64_t q0 = 0; q0 < Q; q0 += kUQ) {
+    const int64_t qn = std::min<int64_t>(kUQ, Q - q0);
+    const int rc = umma_partial_64(planes, sqnorm, N, D, xq + q0 * D, xsq + q0, qn, inv2s2, power, alpha,
+                                   num + q0 * D, z + q0, k_out ? k_out + q0 * N : nullptr, ws, ws_bytes, st);
+    if (rc) return rc;
+  }
+  return SDN_OK;
+}
+
+static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                           const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
+                           float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const UmmaLayout L = umma_layout(N, D);
   if (!ws || ws_bytes < L.total) return SDN_E_WORKSPACE;
   if (!load_encode()) return SDN_E_DEVICE;
@@ -479,33 +523,51 @@ int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, 
   const __nv_bfloat16* hi = static_cast<const __nv_bfloat16*>(planes);
   const __nv_bfloat16* lo = hi + N * D;
 
+  // tensor maps depend only on (planes, workspace, N, D): re-encode when one of those changes
+  struct MapCache { const void* planes; const void* ws; int64_t N, D; CUtensorMap m[6]; bool valid; };
+  static MapCache cache{nullptr, nullptr, 0, 0, {}, false};
+  static std::mutex cache_mu;
   CUtensorMap tm_x, tm_hiA, tm_loA, tm_p, tm_hiB, tm_loB;
-  int rc;
-  if ((rc = make_map(&tm_x, xpl, kUStack, D, kUStack, kUK))) return rc;
-  if ((rc = make_map(&tm_hiA, hi, N, D, kUBankTile, kUK))) return rc;
-  if ((rc = make_map(&tm_loA, lo, N, D, kUBankTile, kUK))) return rc;
-  if ((rc = make_map(&tm_p, P, kUStack, L.npad, kUStack, kUK))) return rc;
-  if ((rc = make_map(&tm_hiB, hi, N, D, kUK, 64))) return rc;
-  if ((rc = make_map(&tm_loB, lo, N, D, kUK, 64))) return rc;
+  {
+    std::lock_guard<std::mutex> lk(cache_mu);
+    if (!(cache.valid && cache.planes == planes && cache.ws == ws && cache.N == N && cache.D == D)) {
+      int rc;
+      cache.valid = false;
+      if ((rc = make_map(&cache.m[0], xpl, kUStack, D, kUStack, kUK))) return rc;
+      if ((rc = make_map(&cache.m[1], hi, N, D, kUBankTile, kUK))) return rc;
+      if ((rc = make_map(&cache.m[2], lo, N, D, kUBankTile, kUK))) return rc;
+      if ((rc = make_map(&cache.m[3], P, L.npad, kUStack, kUK, 64))) return rc;
+      if ((rc = make_map(&cache.m[4], hi, N, D, kUK, 64))) return rc;
+      if ((rc = make_map(&cache.m[5], lo, N, D, kUK, 64))) return rc;
+      cache.planes = planes; cache.ws = ws; cache.N = N; cache.D = D; cache.valid = true;
+    }
+    tm_x = cache.m[0]; tm_hiA = cache.m[1]; tm_loA = cache.m[2]; tm_p = cache.m[3]; tm_hiB = cache.m[4]; tm_loB = cache.m[5];
+  }
 
   // query planes
+  float* zpart = reinterpret_cast<float*>(w + L.off_z);
+  int pid = g_prof.begin("k_umma_xprep", st);
   k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xq, (int)Q, D, xpl);
+  g_prof.end(pid, st);
   SDN_LAUNCHED();
 
   // phase A: split K (= D) so that roughly every SM gets one task
   const int row_tiles = (int)(L.npad / kUBankTile);
   const int kblocks = (int)(D / kUK);
-  int ksplit = std::max(1, std::min(kblocks / 4, (kNumSMs + row_tiles / 2) / row_tiles));
-  ksplit = std::min(ksplit, 32);
-  if (ksplit > 1) SDN_CUDA_OK(cudaMemsetAsync(S_T, 0, (size_t)L.npad * kUStack * 4, st));
-  k_umma_dots<<<dim3(row_tiles, ksplit), kUThreads, kUSmemBytes, st>>>(tm_x, tm_hiA, tm_loA, S_T, kblocks, ksplit,
-                                                                      ksplit > 1 ? 1 : 0);
+  const int64_t split_stride = L.npad * kUStack;
+  pid = g_prof.begin("k_umma_dots", st);
+  k_umma_dots<<<dim3(row_tiles, L.ksplit), kUThreads, kUSmemBytes, st>>>(tm_x, tm_hiA, tm_loA, S_T, split_stride,
+                                                                        kblocks, L.ksplit);
+  g_prof.end(pid, st);
   SDN_LAUNCHED();
 
   // weights
-  SDN_CUDA_OK(cudaMemsetAsync(z, 0, sizeof(float) * Q, st));
-  k_umma_weights<<<(unsigned)(L.npad / 32), 128, 0, st>>>(S_T, sqnorm, xsq, (int)N, L.npad, (int)Q, inv2s2, power,
-                                                         alpha, P, z, k_out);
+  pid = g_prof.begin("k_umma_weights", st);
+  k_umma_weights<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(S_T, split_stride, L.ksplit, sqnorm, xsq, (int)N,
+                                                                      (int)Q, inv2s2, power, alpha, P, zpart, k_out);
+  SDN_LAUNCHED();
+  k_umma_zreduce<<<(unsigned)Q, 256, 0, st>>>(zpart, (int)(L.npad / kWRows), z);
+  g_prof.end(pid, st);
   SDN_LAUNCHED();
 
   // phase B: one CTA per 128 d, bank rows split when that leaves SMs idle
@@ -513,8 +575,10 @@ int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, 
   const int rblocks = (int)(L.npad / kUK);
   int nsplit = std::max(1, std::min(rblocks / 8, kNumSMs / dblocks));
   if (nsplit > 1) SDN_CUDA_OK(cudaMemsetAsync(num, 0, sizeof(float) * Q * D, st));
+  pid = g_prof.begin("k_umma_accum", st);
   k_umma_accum<<<dim3(dblocks, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
                                                                      nsplit, nsplit > 1 ? 1 : 0);
+  g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;
 }

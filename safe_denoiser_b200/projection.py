@@ -92,6 +92,7 @@ class Projector:
         self.path = path
         self.group = group          # torch.distributed group for N-sharded banks (None = single GPU)
         self._scratch = {}
+        self._graphs = {}
 
     # -- scratch -----------------------------------------------------------------------------
     def _get(self, Q: int, need_xq: bool) -> _Scratch:
@@ -180,6 +181,32 @@ class Projector:
             nv.ptr(xf) if apply else None, nv.ptr(neg), nv.ptr(s.denom), nv.ptr(s.gate), nv.ptr(s.mean),
             nv.current_stream()))
         return neg, s
+
+    def correct_graphed(self, x0: torch.Tensor, sigma: float, scale: float, eps: float, **kw):
+        """``correct`` replayed from a CUDA graph: the 6-8 small launches of one projection are launch bound
+        for the shapes the samplers use (N = 515..3000), so the whole call is captured once per
+        (query buffer, arguments) and replayed with one ``cudaGraphLaunch``.  The first call with a given key
+        runs eagerly (it also performs the one-time kernel attribute setup), the second captures, later calls
+        replay.  Not used with a process group (the all-reduce stays outside graphs) nor with ``want_neg`` /
+        ``k_out`` outputs, which callers own."""
+        if self.group is not None or kw.get("want_neg") or kw.get("k_out") is not None:
+            return self.correct(x0, sigma, scale, eps, **kw)
+        key = (x0.data_ptr(), tuple(x0.shape), float(sigma), float(scale), float(eps),
+               tuple(sorted((k, v) for k, v in kw.items())))
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = "seen"
+            return self.correct(x0, sigma, scale, eps, **kw)
+        if entry == "seen":
+            if len(self._graphs) > 64:                      # bound the cache; pointers churn in long runs
+                self._graphs = {key: "seen"}
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.correct(x0, sigma, scale, eps, **kw)
+            entry = (g, out)
+            self._graphs[key] = entry
+        entry[0].replay()
+        return entry[1]
 
     def ddpm_step(self, x_t, eps_pred, z1, z2, coeffs: dict, sigma: float, scale: float, eps: float, *,
                   gate_threshold: float | None = None, return_neg: bool = False, ddim: bool = False,
