@@ -192,7 +192,8 @@ def main():
     sigma, scale, eps = wl["sigma"], wl["scale"], 1e-8
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
+    proj.compute_mean = False      # the logging scalar costs an extra pass on the sharded path; not part of the metric
 
     def step():
         fn = proj.correct_graphed if use_graph else proj.correct
@@ -339,7 +340,10 @@ def main():
                               launch="one CUDA graph replay per step (kernels captured from the eager call)"
                               if use_graph else "eager launches",
                               e2e_call="sdn_conditioning_host (C ABI, pinned host buffers)" if world == 1
-                              else "pinned host -> Projector.correct (N-sharded) -> pinned host")
+                              else "pinned host -> Projector.correct (N-sharded) -> pinned host",
+                              shard_merge=("fused peer-memory kernel (reduce-scatter + correction + all-gather over NVLink)"
+                                           if proj.fused_merge else f"NCCL all-reduce ({proj.fused_merge_error})")
+                              if world > 1 else None)
         line.update({
             "value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "projections/s", "h2d_bytes_per_step": Q * D * 4,

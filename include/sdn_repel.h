@@ -162,6 +162,22 @@ int sdn_epilogue_flow(const float* num, const float* z, int64_t Q, int64_t D,
                       float* latents_out, float* x0c_out, float* denom_out,
                       float* mean_out, void* stream);
 
+/* ---- N-sharded banks: merge + correction in one kernel over NVLink peer memory ------------------------------
+ * Replaces "all-reduce(num|z) then sdn_epilogue_correct" when the bank is sharded by rows over `world` GPUs of one
+ * NVSwitch domain (the reference has no multi-GPU path; this is the exchange step of SURVEY 8e).
+ * peer_packed[p] / peer_out[p] / peer_sig[p] are HOST arrays of `world` device pointers: rank p's partial buffer
+ * [Q*D | Q] fp32 (written by sdn_repel_partial), result buffer [Q*D] fp32 and flag words (uint32 [16], zeroed once),
+ * all peer-mapped in this process (CUDA IPC / symmetric memory).  Rank `rank` reduces D-slice `rank` over all peers
+ * in rank order, applies x0' = x0 - scale * num / (sum_p z_p + eps) and stores the slice into every rank's result
+ * buffer.  `epoch_word` is a local device uint32 initialised to 1 on every rank; the kernel reads the epoch of the
+ * launch from it and advances it, so the call can be replayed from a CUDA graph.  `counter` is a local zeroed uint32.
+ * Every rank must launch the call; waits are bounded (trap after ~seconds). */
+int sdn_shard_merge_correct(const void* const* peer_packed, void* const* peer_out, void* const* peer_sig,
+                            int32_t rank, int32_t world, void* epoch_word, int64_t Q, int64_t D,
+                            float eps, float scale, float gate_threshold, int32_t flags,
+                            const float* x0_local, float* denom_out, int32_t* gate_out, void* counter,
+                            void* stream);
+
 /* ---- SPELL baseline (fast.py:306-340, threshold.py:415-454) ------------------------------
  * dist_out [Q,N] = ||x_q - n_i|| from the same expansion; the force is
  *   term_q = sum_i relu(radius/d_qi - 1) (x_q - n_i) ; x0_inout += scale * term.

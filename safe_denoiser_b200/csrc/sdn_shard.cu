@@ -1,0 +1,149 @@
+// N-sharded banks: ONE kernel that merges the per-rank partial sums over NVLink peer memory and applies the
+// correction -- reduce-scatter, epilogue and all-gather fused (replaces NCCL all-reduce + local epilogue).
+//
+// Every rank r holds num_r [Q,D] | z_r [Q] (its shard's un-normalised sums) in a buffer its peers have mapped.
+// Rank r owns the D-slice r of the result:
+//     for d in slice r:  num = sum_p num_p[q][d]  (peer loads, fixed rank order => bit-identical on every rank)
+//                        x0'[q][d] = x0[q][d] - scale * num / (sum_p z_p[q] + eps)
+//                        store x0'[q][d] into EVERY rank's output buffer (peer stores)
+// so each element crosses NVLink once in and once out -- a two-shot all-reduce with the epilogue in the middle.
+// Cross-GPU ordering uses epoch flags in peer-mapped memory (release/acquire at system scope); every wait is
+// bounded and traps instead of hanging the GPU.  One kernel per rank, each on its own GPU.
+#include <algorithm>
+
+#include "sdn_internal.h"
+
+namespace sdn {
+
+constexpr int kMaxRanks = 8;
+
+struct MergeArgs {
+  const float* packed[kMaxRanks];   // rank p's [Q*D | Q] partial buffer, as mapped here
+  float* out[kMaxRanks];            // rank p's [Q*D] result buffer
+  uint32_t* sig[kMaxRanks];         // rank p's flag words [2 * kMaxRanks]
+  int rank, world;
+  uint32_t* epoch_ptr;              // local device word: epoch of THIS launch; the kernel advances it
+  int64_t Q, D;
+  float eps, scale, gate_thr;
+  int flags;
+  const float* x0;                  // local replicated query [Q,D]
+  float* denom_out;                 // local [Q]
+  int32_t* gate_out;                // local [Q]
+  unsigned int* counter;            // local, zero between launches
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// epochs only grow; compare with wrap-around in mind
+__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t epoch) {
+  for (uint32_t spin = 0;; ++spin) {
+    if ((int32_t)(ld_acquire_sys(p) - epoch) >= 0) return;
+    if (spin > 64u) __nanosleep(64);
+    if (spin > (1u << 22)) __trap();   // seconds: a missing peer must not hang this GPU
+  }
+}
+
+__global__ void __launch_bounds__(256) k_shard_merge_correct(const MergeArgs a) {
+  __shared__ float s_denom;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int64_t q = blockIdx.y;
+  // The epoch lives in device memory so that the launch can be replayed from a CUDA graph: every block reads it
+  // on entry, the last block to finish advances it (all blocks have read it by then).
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_ptr);
+
+  // ---- barrier 1: every rank's partial sums are complete (they were written by earlier kernels of its stream)
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid < a.world) {
+    __threadfence_system();
+    st_release_sys(a.sig[tid] + a.rank, epoch);
+  }
+  if (tid < a.world) spin_until(a.sig[a.rank] + tid, epoch);
+  __syncthreads();
+
+  if (tid == 0) {
+    float z = 0.f;
+    for (int p = 0; p < a.world; ++p) z += __ldcv(a.packed[p] + a.Q * a.D + q);
+    const float denom = z + a.eps;
+    s_denom = denom;
+    if (blockIdx.x == 0) {
+      a.denom_out[q] = denom;
+      a.gate_out[q] = (!(a.flags & SDN_EPI_GATE) || denom > a.gate_thr) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  const float denom = s_denom;
+
+  // ---- my D-slice, in float4 units
+  const int64_t v_all = a.D / 4;
+  const int64_t v0 = v_all * a.rank / a.world, v1 = v_all * (a.rank + 1) / a.world;
+  for (int64_t v = v0 + (int64_t)blockIdx.x * 256 + tid; v < v1; v += (int64_t)gridDim.x * 256) {
+    const int64_t o = q * a.D + v * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < a.world; ++p) {
+      const float4 t = __ldcv(reinterpret_cast<const float4*>(a.packed[p] + o));
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    const float4 x = *reinterpret_cast<const float4*>(a.x0 + o);
+    float4 r;
+    r.x = fmaf(-a.scale, s.x / denom, x.x);
+    r.y = fmaf(-a.scale, s.y / denom, x.y);
+    r.z = fmaf(-a.scale, s.z / denom, x.z);
+    r.w = fmaf(-a.scale, s.w / denom, x.w);
+    for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4*>(a.out[p] + o) = r;
+  }
+
+  // ---- barrier 2: my stores have landed everywhere; leave only when every peer's stores have landed here
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (s_last) {
+    if (tid < a.world) {
+      __threadfence_system();
+      st_release_sys(a.sig[tid] + kMaxRanks + a.rank, epoch);
+      spin_until(a.sig[a.rank] + kMaxRanks + tid, epoch);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      *a.counter = 0;
+      *a.epoch_ptr = epoch + 1;
+    }
+  }
+}
+
+}  // namespace sdn
+
+using namespace sdn;
+
+extern "C" int sdn_shard_merge_correct(const void* const* peer_packed, void* const* peer_out, void* const* peer_sig,
+                                       int32_t rank, int32_t world, void* epoch_word, int64_t Q, int64_t D, float eps,
+                                       float scale, float gate_threshold, int32_t flags, const float* x0_local,
+                                       float* denom_out, int32_t* gate_out, void* counter, void* stream) {
+  if (!peer_packed || !peer_out || !peer_sig || !x0_local || !denom_out || !gate_out || !counter || !epoch_word)
+    return SDN_E_NULL;
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return SDN_E_PARAM;
+  if (Q <= 0 || D <= 0 || Q > 65535) return SDN_E_SHAPE;
+  if (D % 4 != 0 || !aligned16(x0_local)) return SDN_E_ALIGN;
+  MergeArgs a{};
+  for (int p = 0; p < world; ++p) {
+    if (!peer_packed[p] || !peer_out[p] || !peer_sig[p]) return SDN_E_NULL;
+    if (!aligned16(peer_packed[p]) || !aligned16(peer_out[p])) return SDN_E_ALIGN;
+    a.packed[p] = static_cast<const float*>(peer_packed[p]);
+    a.out[p] = static_cast<float*>(peer_out[p]);
+    a.sig[p] = static_cast<uint32_t*>(peer_sig[p]);
+  }
+  a.rank = rank; a.world = world; a.epoch_ptr = static_cast<uint32_t*>(epoch_word); a.Q = Q; a.D = D; a.eps = eps; a.scale = scale;
+  a.gate_thr = gate_threshold; a.flags = flags; a.x0 = x0_local; a.denom_out = denom_out; a.gate_out = gate_out;
+  a.counter = static_cast<unsigned int*>(counter);
+  const int64_t slice_v = D / 4 / world + 1;
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(slice_v, 256), 64));
+  k_shard_merge_correct<<<dim3(gx, (unsigned)Q), 256, 0, (cudaStream_t)stream>>>(a);
+  SDN_LAUNCHED();
+  return SDN_OK;
+}

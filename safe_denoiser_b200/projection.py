@@ -80,8 +80,33 @@ def merge_partials(packed: torch.Tensor, group) -> torch.Tensor:
     return packed
 
 
+class ShardLink:
+    """Peer-mapped buffers of one N-sharded projection shape (torch symmetric memory = CUDA VMM/IPC handles
+    exchanged over the process group).  ``packed`` receives this rank's partial sums, ``out`` the merged,
+    corrected query; ``sig`` holds the epoch flags of sdn_shard_merge_correct."""
+
+    def __init__(self, Q: int, D: int, group, device):
+        import ctypes as C
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.packed = symm.empty(Q * D + Q, dtype=torch.float32, device=device)
+        self.out = symm.empty(Q * D, dtype=torch.float32, device=device)
+        self.sig = symm.empty(64, dtype=torch.int32, device=device)
+        self.sig.zero_()
+        handles = [symm.rendezvous(t, group) for t in (self.packed, self.out, self.sig)]
+        arr = C.c_void_p * self.world
+        self.p_packed, self.p_out, self.p_sig = (arr(*[int(p) for p in h.buffer_ptrs]) for h in handles)
+        self._handles = handles
+        self.counter = torch.zeros(4, dtype=torch.int32, device=device)
+        self.epoch = torch.ones(4, dtype=torch.int32, device=device)    # advanced by the kernel itself
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # every rank's flag words are zero before the first merge
+
+
 class _Scratch:
-    __slots__ = ("num", "z", "xsq", "xq", "denom", "gate", "mean", "ws", "ws_bytes", "packed")
+    __slots__ = ("num", "z", "xsq", "xq", "denom", "gate", "mean", "ws", "ws_bytes", "packed", "link")
 
 
 class Projector:
@@ -91,6 +116,9 @@ class Projector:
         self.bank = bank
         self.path = path
         self.group = group          # torch.distributed group for N-sharded banks (None = single GPU)
+        self.fused_merge = group is not None    # merge + correction in one kernel over NVLink peer memory
+        self.fused_merge_error = None
+        self.compute_mean = True                # the reference's logging scalar (extra pass when sharded)
         self._scratch = {}
         self._graphs = {}
 
@@ -100,8 +128,15 @@ class Projector:
         if s is None:
             dev, D = self.bank.device, self.bank.D
             s = _Scratch()
-            # num and z live in one packed [Q, D+1]-sized buffer so the N-shard merge is ONE all-reduce
-            s.packed = torch.empty(Q * D + Q, dtype=torch.float32, device=dev)
+            s.link = None
+            if self.group is not None and self.fused_merge:
+                try:
+                    s.link = ShardLink(Q, D, self.group, dev)
+                except Exception as e:           # no peer mapping on this box: NCCL all-reduce instead
+                    self.fused_merge = False
+                    self.fused_merge_error = repr(e)
+            # num and z live in one packed [Q, D+1]-sized buffer so the N-shard merge is ONE exchange
+            s.packed = s.link.packed if s.link is not None else torch.empty(Q * D + Q, dtype=torch.float32, device=dev)
             s.num = s.packed[: Q * D].view(Q, D)
             s.z = s.packed[Q * D:]
             s.xsq = torch.empty(Q, dtype=torch.float32, device=dev)
@@ -131,7 +166,7 @@ class Projector:
     def partial_sums(self, x0: torch.Tensor, sigma: float, *, normalize_channels: int = 0,
                      model_out: torch.Tensor | None = None, c_x: float = 1.0, c_m: float = 0.0,
                      x0_out: torch.Tensor | None = None, dist_power: int = 1, bank_alpha: float = 1.0,
-                     k_out: torch.Tensor | None = None, z_only: bool = False) -> _Scratch:
+                     k_out: torch.Tensor | None = None, z_only: bool = False, merge: bool = True) -> _Scratch:
         """num[Q,D] = sum_i k_qi n_i and z[Q] = sum_i k_qi over this (shard of the) bank, merged over
         the process group when the bank is N-sharded.  ``x0`` contiguous fp32 [Q,...]."""
         L = nv.lib()
@@ -159,7 +194,8 @@ class Projector:
                                      1.0 / (2.0 * float(sigma) ** 2), int(dist_power), float(bank_alpha),
                                      None if z_only else nv.ptr(s.num), nv.ptr(s.z), nv.ptr(k_out),
                                      nv.ptr(s.ws), s.ws_bytes, self.path, st))
-        merge_partials(s.z if z_only else s.packed, self.group)
+        if merge:
+            merge_partials(s.z if z_only else s.packed, self.group)
         return s
 
     # -- step 3: epilogues ---------------------------------------------------------------------
@@ -169,9 +205,13 @@ class Projector:
                 bank_alpha: float = 1.0, k_out: torch.Tensor | None = None):
         """conditioning(): x0 <- x0 - scale * neg in place.  Returns (neg or None, scratch); scratch
         holds denom [Q], gate [Q] (int32), mean [1] and num [Q,D] as device tensors."""
-        s = self.partial_sums(x0, sigma, normalize_channels=normalize_channels,
-                              dist_power=dist_power, bank_alpha=bank_alpha, k_out=k_out)
         Q, xf = self._flat_query(x0)
+        fused = (self.group is not None and self.fused_merge and apply and not want_neg
+                 and self._get(Q, normalize_channels > 0).link is not None)
+        s = self.partial_sums(x0, sigma, normalize_channels=normalize_channels,
+                              dist_power=dist_power, bank_alpha=bank_alpha, k_out=k_out, merge=not fused)
+        if fused:
+            return None, self._merge_correct(s, xf, Q, scale, eps, gate_threshold)
         neg = torch.empty_like(xf) if want_neg else None
         s.mean.zero_()
         flags = nv.EPI_GATE if gate_threshold is not None else 0
@@ -182,6 +222,20 @@ class Projector:
             nv.current_stream()))
         return neg, s
 
+    def _merge_correct(self, s, xf, Q, scale, eps, gate_threshold):
+        """N-sharded: reduce-scatter + correction + all-gather in one kernel over peer memory."""
+        link = s.link
+        flags = nv.EPI_GATE if gate_threshold is not None else 0
+        nv.check(nv.lib().sdn_shard_merge_correct(
+            link.p_packed, link.p_out, link.p_sig, link.rank, link.world, nv.ptr(link.epoch), Q, self.bank.D,
+            float(eps), float(scale), float(gate_threshold if gate_threshold is not None else 0.0), flags,
+            nv.ptr(xf), nv.ptr(s.denom), nv.ptr(s.gate), nv.ptr(link.counter), nv.current_stream()))
+        merged = link.out.view(Q, self.bank.D)
+        if self.compute_mean:
+            s.mean.copy_(((xf - merged) / (scale if scale != 0 else 1.0)).clamp_(-1e10, 1e10).mean().reshape(1))
+        xf.copy_(merged)
+        return s
+
     def correct_graphed(self, x0: torch.Tensor, sigma: float, scale: float, eps: float, **kw):
         """``correct`` replayed from a CUDA graph: the 6-8 small launches of one projection are launch bound
         for the shapes the samplers use (N = 515..3000), so the whole call is captured once per
@@ -189,8 +243,8 @@ class Projector:
         runs eagerly (it also performs the one-time kernel attribute setup), the second captures, later calls
         replay.  Not used with a process group (the all-reduce stays outside graphs) nor with ``want_neg`` /
         ``k_out`` outputs, which callers own."""
-        if self.group is not None or kw.get("want_neg") or kw.get("k_out") is not None:
-            return self.correct(x0, sigma, scale, eps, **kw)
+        if (self.group is not None and not self.fused_merge) or kw.get("want_neg") or kw.get("k_out") is not None:
+            return self.correct(x0, sigma, scale, eps, **kw)       # an NCCL all-reduce stays outside graphs
         key = (x0.data_ptr(), tuple(x0.shape), float(sigma), float(scale), float(eps),
                tuple(sorted((k, v) for k, v in kw.items())))
         entry = self._graphs.get(key)
