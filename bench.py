@@ -197,7 +197,7 @@ def main():
 
     def step():
         fn = proj.correct_graphed if use_graph else proj.correct
-        fn(x, sigma, scale, eps, normalize_channels=normalize,
+        fn(x, sigma, scale, eps, normalize_channels=normalize, want_num=False,
            gate_threshold=(1.0 if wl["kind"] == "threshold" else None))
 
     def barrier():

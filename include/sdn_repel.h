@@ -162,6 +162,22 @@ int sdn_epilogue_flow(const float* num, const float* z, int64_t Q, int64_t D,
                       float* latents_out, float* x0c_out, float* denom_out,
                       float* mean_out, void* stream);
 
+/* ---- conditioning() with the fewest launches (one GPU) ------------------------------------------------------
+ * = sdn_query_prepare + sdn_repel_partial + sdn_epilogue_correct for a query that needs no eps->x0 conversion and
+ * no channel normalisation (fast.py:120-132, threshold.py:171-193).
+ *   Q <= 8 : the one-pass kernel computes ||x||^2 itself and the per-cluster reduction applies the correction
+ *            (2 launches);
+ *   Q > 8  : (needs `planes` and z_out) query planes + ||x||^2 in one kernel, correction fused into the epilogue
+ *            of phase B (5 launches instead of 8).
+ * x0_inout [Q,D] is corrected in place; num_out / neg_out / k_out are optional extra outputs; mean_out is zeroed
+ * by the call.  Returns SDN_E_UNSUPPORTED for shapes neither fused path takes (callers then use the three-call
+ * sequence).  Workspace: sdn_repel_workspace_bytes(Q, N, D, SDN_PATH_AUTO). */
+int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* planes, int64_t N, int64_t D,
+                           float* x0_inout, int64_t Q, float inv_two_sigma_sq, int32_t dist_power, float bank_alpha,
+                           float eps, float scale, float gate_threshold, int32_t flags,
+                           float* num_out, float* z_out, float* neg_out, float* denom_out, int32_t* gate_out,
+                           float* mean_out, float* k_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- N-sharded banks: merge + correction in one kernel over NVLink peer memory ------------------------------
  * Replaces "all-reduce(num|z) then sdn_epilogue_correct" when the bank is sharded by rows over `world` GPUs of one
  * NVSwitch domain (the reference has no multi-GPU path; this is the exchange step of SURVEY 8e).

@@ -34,6 +34,8 @@ SIGNATURES = {
     "sdn_epilogue_ddim": (C.c_int, [_p, _p, _i64, _i64, _f, _f, _f, _i32, _p, _p, _p,
                                     _f, _f, _f, _f, _p, _p, _p, _p, _p, _p]),
     "sdn_epilogue_flow": (C.c_int, [_p, _p, _i64, _i64, _f, _f, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p]),
+    "sdn_conditioning_fused": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _f, _i32, _f, _f, _f, _f, _i32,
+                                         _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sdn_shard_merge_correct": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i64, _i64, _f, _f, _f, _i32,
                                           _p, _p, _p, _p, _p]),
     "sdn_sparse_repel": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _f, _f, _p, _p, _p, _sz, _p]),

@@ -118,6 +118,31 @@ int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes
   return rc;
 }
 
+int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* planes, int64_t N, int64_t D,
+                           float* x0_inout, int64_t Q, float inv_two_sigma_sq, int32_t dist_power, float bank_alpha,
+                           float eps, float scale, float gate_threshold, int32_t flags, float* num_out, float* z_out,
+                           float* neg_out, float* denom_out, int32_t* gate_out, float* mean_out, float* k_out,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (!sqnorm || !x0_inout || (!bank && !planes)) return SDN_E_NULL;
+  if (Q <= 0 || N <= 0 || D <= 0) return SDN_E_SHAPE;
+  if (dist_power != 1 && dist_power != 2) return SDN_E_PARAM;
+  if (D % 4 != 0 || (bank && !aligned16(bank)) || !aligned16(x0_inout) || (num_out && !aligned16(num_out)) ||
+      (neg_out && !aligned16(neg_out)))
+    return SDN_E_ALIGN;
+  g_prof.reset();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Q > 8 && planes && z_out && umma_supported(Q, N, D, planes)) {
+    if (!workspace || workspace_bytes < umma_workspace_bytes(Q, N, D)) return SDN_E_WORKSPACE;
+    return umma_conditioning(planes, sqnorm, N, D, x0_inout, Q, inv_two_sigma_sq, dist_power, bank_alpha, eps, scale,
+                             gate_threshold, flags, num_out, z_out, neg_out, denom_out, gate_out, mean_out, k_out,
+                             workspace, workspace_bytes, st);
+  }
+  if (!bank || !stream_supported(Q, N, D)) return SDN_E_UNSUPPORTED;
+  return stream_conditioning(bank, sqnorm, N, D, x0_inout, x0_inout, Q, inv_two_sigma_sq, dist_power, bank_alpha, eps,
+                             scale, gate_threshold, flags, num_out, z_out, neg_out, denom_out, gate_out, mean_out,
+                             k_out, workspace, workspace_bytes, st);
+}
+
 int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t D, float* x0_inout,
                      const float* xsq, int64_t Q, float radius, float scale, float* term_out,
                      float* wsum_out, void* workspace, size_t workspace_bytes, void* stream) {

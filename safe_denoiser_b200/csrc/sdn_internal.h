@@ -27,11 +27,23 @@ int stream_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D,
                    const float* xsq, int64_t Q, float inv_two_sigma_sq, int power, float alpha,
                    float* num, float* z, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// one-pass projection + correction in two launches (||x||^2 in-kernel, reduce fused with the epilogue)
+int stream_conditioning(const float* bank, const float* sqnorm, int64_t N, int64_t D, float* x0_inout,
+                        const float* xq, int64_t Q, float inv_two_sigma_sq, int power, float alpha, float eps,
+                        float scale, float gate_thr, int flags, float* num_out, float* z_out, float* neg_out,
+                        float* denom_out, int32_t* gate_out, float* mean_out, float* k_out, void* ws,
+                        size_t ws_bytes, cudaStream_t st);
+
 // ---- tcgen05 two-phase path for batched calls (sdn_umma.cu) ----
 bool umma_supported(int64_t Q, int64_t N, int64_t D, const void* planes);
 size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D);
 int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                  const float* xsq, int64_t Q, float inv_two_sigma_sq, int power, float alpha,
                  float* num, float* z, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+int umma_conditioning(const void* planes, const float* sqnorm, int64_t N, int64_t D, float* x0_inout, int64_t Q,
+                      float inv_two_sigma_sq, int power, float alpha, float eps, float scale, float gate_thr,
+                      int flags, float* num_out, float* z, float* neg_out, float* denom_out, int32_t* gate_out,
+                      float* mean_out, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace sdn

@@ -67,6 +67,12 @@ __device__ __forceinline__ void st_async_remote(float* local_addr, uint64_t* loc
                ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
 }
 
+__device__ __forceinline__ void st_remote(float* local_addr, uint32_t peer, float v) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_addr)), "r"(peer));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+
 // Sum V per-lane values across the warp with a reduce-scatter butterfly (V-1 shuffles instead of 5V).
 // On return, lane l holds in v[0] the warp total of value index `warp_value_index<V>(l)`.
 template <int V>
@@ -107,11 +113,12 @@ __device__ __forceinline__ bool warp_value_owner(int lane) {
 
 struct StreamArgs {
   const float* bank; const float* sqnorm; int64_t N; int64_t D;
-  const float* x; const float* xsq; int q_real;
+  const float* x; const float* xsq; int q_real;   // xsq == nullptr: ||x||^2 is computed in the kernel
   float inv2s2; int power; float alpha;
   float* part_num;   // [clusters][q_real][D]
   float* part_z;     // [clusters][q_real]
   float* k_out;      // [q_real][N] or null
+  float* zero_word;  // optional scalar cleared by CTA 0 (the logging mean of the fused epilogue), or null
 };
 
 template <int Q, int VPT, int TN>
@@ -123,6 +130,7 @@ constexpr size_t stream_smem_bytes() {
          + 3 * kStMaxCluster * V * 4         // receive slots
          + 2 * V * 4                         // k of the tiles being accumulated, double buffered
          + 64 * 4                            // z reduction scratch
+         + kStMaxCluster * 8 * 4             // per-CTA ||x slice||^2 partials
          + (2 * kStStages + 2 + 2 + 3) * 8 + 64;   // mbarriers + alignment slack
 }
 
@@ -138,7 +146,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
   float* recv = wp + 2 * kStCWarps * V;                               // [3][kStMaxCluster][V]
   float* ks = recv + 3 * kStMaxCluster * V;                           // [2][V]
   float* zred = ks + 2 * V;                                           // [64]
-  uint64_t* full = reinterpret_cast<uint64_t*>(zred + 64);            // [stages]  TMA landed
+  float* xsp = zred + 64;                                             // [kStMaxCluster][8]
+  uint64_t* full = reinterpret_cast<uint64_t*>(xsp + kStMaxCluster * 8);   // [stages]  TMA landed
   uint64_t* empty = full + kStStages;                                 // [stages]  all compute warps done with the stage
   uint64_t* pr = empty + kStStages;                                   // [2]       warp partials of a tile written
   uint64_t* kr = pr + 2;                                              // [2]       weights of a tile written
@@ -161,7 +170,49 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // every CTA of the cluster has initialised its barriers before any remote store can target them
+  // The first tiles only touch this CTA's own shared memory: start them now so that their HBM latency overlaps
+  // the ||x||^2 exchange and the start-up cluster barrier (the kernel is ramp-bound at N ~ 500).
+  const int nprefetch = min(ntiles, kStStages);
+  if (warp == kStCWarps && lane == 0) {
+    const float* slice0 = a.bank + (int64_t)crank * SLICE;
+    for (int t = 0; t < nprefetch; ++t) {
+      const int64_t r0 = lo + (int64_t)t * TN;
+      const int rows = (int)min((int64_t)TN, hi - r0);
+      mbar_expect_tx(&full[t], (uint32_t)(rows * SLICE * 4));
+      for (int r = 0; r < rows; ++r)
+        bulk_g2s(tiles + ((size_t)t * TN + r) * SLICE, slice0 + (r0 + r) * a.D, SLICE * 4, &full[t]);
+    }
+  }
+  if (a.zero_word && blockIdx.x == 0 && tid == 0) *a.zero_word = 0.f;
+  if (a.xsq == nullptr) {
+    // ||x_q||^2 in the kernel: every CTA squares its slice, the per-CTA partials cross the cluster through
+    // distributed shared memory and become visible with the start-up cluster barrier below
+    float loc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      loc[q] = 0.f;
+      if (warp < kStCWarps) {
+        const int qs = min(q, a.q_real - 1);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          const float4 t = *reinterpret_cast<const float4*>(a.x + (int64_t)qs * a.D + (int64_t)crank * SLICE +
+                                                            (v * kStCompute + tid) * 4);
+          loc[q] = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, loc[q]))));
+        }
+      }
+      loc[q] = warp_sum(loc[q]);
+      if (lane == 0 && warp < kStCWarps) wp[warp * Q + q] = loc[q];
+    }
+    __syncthreads();
+    if (tid < Q) {
+      float tot = 0.f;
+      for (int w = 0; w < kStCWarps; ++w) tot += wp[w * Q + tid];
+      for (uint32_t peer = 0; peer < csize; ++peer) st_remote(xsp + crank * 8 + tid, peer, tot);
+    }
+    __syncthreads();
+  }
+  // every CTA of the cluster has initialised its barriers (and delivered its ||x||^2 partial) before any
+  // remote store can target them
   cluster_arrive();
   cluster_wait();
 
@@ -169,9 +220,9 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const float* slice0 = a.bank + (int64_t)crank * SLICE;
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = nprefetch; t < ntiles; ++t) {
         const int s = t % kStStages;
-        if (t >= kStStages) mbar_wait(&empty[s], (uint32_t)(((t / kStStages) + 1) & 1));
+        mbar_wait(&empty[s], (uint32_t)(((t / kStStages) + 1) & 1));
         const int64_t r0 = lo + (int64_t)t * TN;
         const int rows = (int)min((int64_t)TN, hi - r0);
         mbar_expect_tx(&full[s], (uint32_t)(rows * SLICE * 4));
@@ -183,7 +234,12 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
     // =========================== weights ===========================
     if (lane < V) {
       const int r = lane / Q, q = lane % Q;
-      const float xs_q = a.xsq[min(q, a.q_real - 1)];
+      float xs_q = 0.f;
+      if (a.xsq) {
+        xs_q = a.xsq[min(q, a.q_real - 1)];
+      } else {
+        for (uint32_t src = 0; src < csize; ++src) xs_q += xsp[src * 8 + q];
+      }
       float zacc = 0.f;
       for (int t = 0; t < ntiles; ++t) {
         const int64_t r0 = lo + (int64_t)t * TN;
@@ -347,6 +403,67 @@ k_stream_reduce(const float* __restrict__ part_num, const float* __restrict__ pa
   }
 }
 
+// Same reduction with the correction applied on the fly (single GPU, Q <= 8): x0 <- x0 - scale * num / (z + eps).
+// Saves the num round trip and two launches; num / neg / z are still written when the caller wants them.
+struct ReduceCorrectArgs {
+  const float* part_num; const float* part_z; int ncl; int64_t D; int Q;
+  float eps, scale, gate_thr; int flags;
+  float* x0; float* num_out; float* z_out; float* neg_out; float* denom_out; int32_t* gate_out; float* mean_out;
+};
+
+__global__ void __launch_bounds__(256) k_stream_reduce_correct(const ReduceCorrectArgs a) {
+  __shared__ float4 sh[8][32];
+  __shared__ float red[33];
+  const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int64_t q = blockIdx.y;
+  const int64_t QD = (int64_t)a.Q * a.D;
+  const int64_t j = ((int64_t)blockIdx.x * 32 + col) * 4;
+  float z = 0.f;
+  for (int c = 0; c < a.ncl; ++c) z += a.part_z[(int64_t)c * a.Q + q];
+  const float denom = z + a.eps;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (a.z_out) a.z_out[q] = z;
+    if (a.denom_out) a.denom_out[q] = denom;
+    if (a.gate_out) a.gate_out[q] = (!(a.flags & SDN_EPI_GATE) || denom > a.gate_thr) ? 1 : 0;
+  }
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < a.D) {
+#pragma unroll 4
+    for (int c = grp; c < a.ncl; c += 8) {
+      const float4 p = ld_stream4(a.part_num + (int64_t)c * QD + q * a.D + j);
+      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+  }
+  sh[grp][col] = s;
+  __syncthreads();
+  float msum = 0.f;
+  if (grp == 0 && j < a.D) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) {
+      const float4 p = sh[g][col];
+      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    const int64_t o = q * a.D + j;
+    if (a.num_out) *reinterpret_cast<float4*>(a.num_out + o) = s;
+    const float4 n = make_float4(s.x / denom, s.y / denom, s.z / denom, s.w / denom);
+    if (a.neg_out) *reinterpret_cast<float4*>(a.neg_out + o) = n;
+    if (a.x0) {
+      float4 x = *reinterpret_cast<const float4*>(a.x0 + o);
+      x.x = fmaf(-a.scale, n.x, x.x);
+      x.y = fmaf(-a.scale, n.y, x.y);
+      x.z = fmaf(-a.scale, n.z, x.z);
+      x.w = fmaf(-a.scale, n.w, x.w);
+      *reinterpret_cast<float4*>(a.x0 + o) = x;
+    }
+    msum = fminf(fmaxf(n.x, -1e10f), 1e10f) + fminf(fmaxf(n.y, -1e10f), 1e10f) +
+           fminf(fmaxf(n.z, -1e10f), 1e10f) + fminf(fmaxf(n.w, -1e10f), 1e10f);
+  }
+  if (a.mean_out) {
+    msum = block_sum(msum, red);
+    if (threadIdx.x == 0) atomicAdd(a.mean_out, msum / (float)QD);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 struct StreamPlan {
   int qt = 0, vpt = 0, tn = 0, cs = 0;   // template instance and cluster size
@@ -427,16 +544,16 @@ size_t stream_workspace_bytes(int64_t Q, int64_t N, int64_t D) {
   return ncl * (size_t)Q * D * 4 + ncl * (size_t)Q * 4 + 256;
 }
 
-int stream_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D, const float* xq,
-                   const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
-                   float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int stream_launch(const float* bank, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                         const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* k_out,
+                         float* zero_word, void* ws, size_t ws_bytes, cudaStream_t st, StreamArgs* a_out, int* ncl_out) {
   const StreamPlan p = plan_stream(Q, N, D);
   if (!p.ok) return SDN_E_UNSUPPORTED;
   if (!ws || ws_bytes < stream_workspace_bytes(Q, N, D)) return SDN_E_WORKSPACE;
   const int hint = max_clusters_for(p.cs);
   StreamArgs a{};
   a.bank = bank; a.sqnorm = sqnorm; a.N = N; a.D = D; a.x = xq; a.xsq = xsq; a.q_real = (int)Q;
-  a.inv2s2 = inv2s2; a.power = power; a.alpha = alpha; a.k_out = k_out;
+  a.inv2s2 = inv2s2; a.power = power; a.alpha = alpha; a.k_out = k_out; a.zero_word = zero_word;
   a.part_num = static_cast<float*>(ws);
   a.part_z = a.part_num + (size_t)hint * Q * D;
   int ncl = 0, rc = SDN_E_UNSUPPORTED;
@@ -448,10 +565,42 @@ int stream_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D,
   SDN_ST_CASE(1, 4, 1) SDN_ST_CASE(2, 4, 1)
 #undef SDN_ST_CASE
   g_prof.end(pid, st);
+  *a_out = a;
+  *ncl_out = ncl;
+  return rc;
+}
+
+int stream_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                   const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
+                   float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  StreamArgs a{};
+  int ncl = 0;
+  const int rc = stream_launch(bank, sqnorm, N, D, xq, xsq, Q, inv2s2, power, alpha, k_out, nullptr, ws, ws_bytes, st,
+                               &a, &ncl);
   if (rc) return rc;
   const int64_t QD = Q * D;
-  pid = g_prof.begin("k_stream_reduce", st);
+  const int pid = g_prof.begin("k_stream_reduce", st);
   k_stream_reduce<<<(unsigned)cdiv(QD, 128), 256, 0, st>>>(a.part_num, a.part_z, ncl, QD, (int)Q, num, z);
+  g_prof.end(pid, st);
+  SDN_LAUNCHED();
+  return SDN_OK;
+}
+
+int stream_conditioning(const float* bank, const float* sqnorm, int64_t N, int64_t D, float* x0_inout,
+                        const float* xq, int64_t Q, float inv2s2, int power, float alpha, float eps, float scale,
+                        float gate_thr, int flags, float* num_out, float* z_out, float* neg_out, float* denom_out,
+                        int32_t* gate_out, float* mean_out, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  StreamArgs a{};
+  int ncl = 0;
+  const int rc = stream_launch(bank, sqnorm, N, D, xq, nullptr, Q, inv2s2, power, alpha, k_out, mean_out, ws, ws_bytes,
+                               st, &a, &ncl);
+  if (rc) return rc;
+  ReduceCorrectArgs r{};
+  r.part_num = a.part_num; r.part_z = a.part_z; r.ncl = ncl; r.D = D; r.Q = (int)Q; r.eps = eps; r.scale = scale;
+  r.gate_thr = gate_thr; r.flags = flags; r.x0 = x0_inout; r.num_out = num_out; r.z_out = z_out; r.neg_out = neg_out;
+  r.denom_out = denom_out; r.gate_out = gate_out; r.mean_out = mean_out;
+  const int pid = g_prof.begin("k_stream_reduce_correct", st);
+  k_stream_reduce_correct<<<dim3((unsigned)cdiv(D, 128), (unsigned)Q), 256, 0, st>>>(r);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;

@@ -160,6 +160,38 @@ k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
   *reinterpret_cast<uint2*>(planes + (int64_t)(kUQ + q) * D + j) = *reinterpret_cast<const uint2*>(l);
 }
 
+// Same, plus ||x_q||^2 partials (one per 1024-element chunk, summed by k_umma_weights) so that the batched
+// conditioning call needs no separate query-prepare launch.  grid (D/1024, 64).
+__global__ void __launch_bounds__(256)
+k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes,
+             float* __restrict__ xsq_part, float* __restrict__ zero_word) {
+  __shared__ float red[33];
+  if (zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *zero_word = 0.f;
+  const int q = blockIdx.y;
+  const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  float ss = 0.f;
+  if (j < D) {
+    __nv_bfloat16 h[4], l[4];
+    if (q < Q) {
+      const float4 v = *reinterpret_cast<const float4*>(xq + (int64_t)q * D + j);
+      const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        h[u] = __float2bfloat16_rn(f[u]);
+        l[u] = __float2bfloat16_rn(f[u] - __bfloat162float(h[u]));
+        ss = fmaf(f[u], f[u], ss);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) h[u] = l[u] = __float2bfloat16_rn(0.f);
+    }
+    *reinterpret_cast<uint2*>(planes + (int64_t)q * D + j) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(planes + (int64_t)(kUQ + q) * D + j) = *reinterpret_cast<const uint2*>(l);
+  }
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0) xsq_part[(int64_t)blockIdx.x * kUQ + q] = ss;
+}
+
 // ------------------------------------------------------------------------------------------ phase A
 // grid (row tiles, k splits).  S_T [ksplit][Npad][128] fp32: S_T[s][i][r] = sum over split s of X[r][d] * bank[i][d].
 //
@@ -280,8 +312,9 @@ constexpr int kWRows = 4;
 
 __global__ void __launch_bounds__(kWRows * kUQ)
 k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, const float* __restrict__ sqnorm,
-               const float* __restrict__ xsq, int N, int Q, float inv2s2, int power, float alpha,
-               __nv_bfloat16* __restrict__ P, float* __restrict__ zpart, float* __restrict__ k_out) {
+               const float* __restrict__ xsq, const float* __restrict__ xsq_part, int xsq_nparts, int N, int Q,
+               float inv2s2, int power, float alpha, __nv_bfloat16* __restrict__ P, float* __restrict__ zpart,
+               float* __restrict__ k_out) {
   __shared__ float zs[kWRows][kUQ];
   const int q = threadIdx.x & (kUQ - 1);
   const int rsub = threadIdx.x >> 6;
@@ -294,7 +327,15 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
     dot += p[q] + p[kUQ + q];
   }
   float k = 0.f;
-  if (i < N && q < Q) k = expf(-dist_from_dot(xsq[q], sqnorm[i], dot, alpha, power) * inv2s2);
+  if (i < N && q < Q) {
+    float xs = 0.f;
+    if (xsq) {
+      xs = xsq[q];
+    } else {
+      for (int c = 0; c < xsq_nparts; ++c) xs += xsq_part[(int64_t)c * kUQ + q];
+    }
+    k = expf(-dist_from_dot(xs, sqnorm[i], dot, alpha, power) * inv2s2);
+  }
   const __nv_bfloat16 h = __float2bfloat16_rn(k);
   const __nv_bfloat16 l = __float2bfloat16_rn(k - __bfloat162float(h));
   P[(int64_t)i * kUStack + q] = h;
@@ -324,11 +365,18 @@ k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------ phase B
+// Optional correction fused into phase B's epilogue (one GPU, no bank-row split): x0 -= scale * num / (z + eps).
+struct AccumEpi {
+  const float* z;       // null: no fused correction
+  float eps, scale, gate_thr; int flags;
+  float* x0; float* neg_out; float* denom_out; int32_t* gate_out; float* mean_out; float inv_qd;
+};
+
 // grid (D / 128, n splits).  num[q][d] (+)= sum_i P[q][i] * (hi+lo)[i][d] over this split's bank rows.
 __global__ void __launch_bounds__(kUThreads, 1)
 k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
              const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
-             int rblocks_total, int nsplit, int use_atomic) {
+             int rblocks_total, int nsplit, int use_atomic, const AccumEpi epi) {
   extern __shared__ unsigned char smem_raw[];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -395,19 +443,53 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     u_fence_after();
     const int64_t d = (int64_t)d0 + lq * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);
+    float msum = 0.f;
 #pragma unroll 1
     for (int c = 0; c < kUQ / 32; ++c) {
       float a[32], b[32];
       u_tmem_ld32(tl + (uint32_t)(c * 32), a);            // hi*P_hi + lo*P_hi, queries [32c, 32c+32)
       u_tmem_ld32(tl + (uint32_t)(kUQ + c * 32), b);      // hi*P_lo
+      if (epi.z) {
+        // all loads of the chunk first: the stores below may alias them as far as the compiler knows, and one
+        // load -> store round trip per query row costs ~25 us per launch
+        float xv[32], dn[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int q = c * 32 + j;
-        if (q < Q) {
-          float* o = num + (int64_t)q * D + d;
-          if (use_atomic) atomicAdd(o, a[j] + b[j]); else *o = a[j] + b[j];
+        for (int j = 0; j < 32; ++j) {
+          const int q = min(c * 32 + j, Q - 1);
+          dn[j] = __ldg(epi.z + q) + epi.eps;
+          xv[j] = epi.x0 ? __ldcg(epi.x0 + (int64_t)q * D + d) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int q = c * 32 + j;
+          if (q < Q) {
+            const float v = a[j] + b[j];
+            const int64_t o = (int64_t)q * D + d;
+            const float n = v / dn[j];
+            if (num) num[o] = v;
+            if (epi.neg_out) epi.neg_out[o] = n;
+            if (epi.x0) epi.x0[o] = fmaf(-epi.scale, n, xv[j]);
+            msum += fminf(fmaxf(n, -1e10f), 1e10f);
+            if (blockIdx.x == 0 && lq == 0 && lane == 0) {
+              if (epi.denom_out) epi.denom_out[q] = dn[j];
+              if (epi.gate_out) epi.gate_out[q] = (!(epi.flags & SDN_EPI_GATE) || dn[j] > epi.gate_thr) ? 1 : 0;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int q = c * 32 + j;
+          if (q < Q) {
+            float* o = num + (int64_t)q * D + d;
+            if (use_atomic) atomicAdd(o, a[j] + b[j]); else *o = a[j] + b[j];
+          }
         }
       }
+    }
+    if (epi.z && epi.mean_out) {
+      msum = warp_sum(msum);
+      if (lane == 0) atomicAdd(epi.mean_out, msum * epi.inv_qd);
     }
   }
   u_fence_before();
@@ -456,7 +538,7 @@ int umma_ksplit(int64_t npad, int64_t D) {
 struct UmmaLayout {
   int64_t npad;        // bank rows padded to 128
   int ksplit;
-  size_t off_x, off_s, off_p, off_z, total;
+  size_t off_x, off_s, off_p, off_z, off_q, total;
 };
 UmmaLayout umma_layout(int64_t N, int64_t D) {
   UmmaLayout L;
@@ -470,6 +552,8 @@ UmmaLayout umma_layout(int64_t N, int64_t D) {
   L.off_p = o; o += (size_t)kUStack * L.npad * 2;            // P planes
   o = (o + 255) / 256 * 256;
   L.off_z = o; o += (size_t)(L.npad / kWRows) * kUQ * 4 + 256;   // per-block z partials + completion counter
+  o = (o + 255) / 256 * 256;
+  L.off_q = o; o += (size_t)cdiv(D, 1024) * kUQ * 4;          // ||x||^2 partials of the fused query prepare
   L.total = (o + 255) / 256 * 256;
   return L;
 }
@@ -487,7 +571,8 @@ size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D) {
 
 static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                            const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
-                           float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                           float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, const AccumEpi* epi,
+                           float* zero_word);
 
 // More than 64 query rows: one two-phase pass over the bank per group of 64 (the TMEM accumulator of phase B
 // holds 128 d x 128 stacked query columns).
@@ -498,7 +583,35 @@ int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, 
   for (int64_t q0 = 0; q0 < Q; q0 += kUQ) {
     const int64_t qn = std::min<int64_t>(kUQ, Q - q0);
     const int rc = umma_partial_64(planes, sqnorm, N, D, xq + q0 * D, xsq + q0, qn, inv2s2, power, alpha,
-                                   num + q0 * D, z + q0, k_out ? k_out + q0 * N : nullptr, ws, ws_bytes, st);
+                                   num + q0 * D, z + q0, k_out ? k_out + q0 * N : nullptr, ws, ws_bytes, st, nullptr,
+                                   nullptr);
+    if (rc) return rc;
+  }
+  return SDN_OK;
+}
+
+// conditioning() for batched queries on one GPU: query planes + ||x||^2 in one kernel, correction fused into
+// phase B's epilogue.  z must be a valid [Q] buffer (scratch if the caller does not want it).
+int umma_conditioning(const void* planes, const float* sqnorm, int64_t N, int64_t D, float* x0_inout, int64_t Q,
+                      float inv2s2, int power, float alpha, float eps, float scale, float gate_thr, int flags,
+                      float* num_out, float* z, float* neg_out, float* denom_out, int32_t* gate_out, float* mean_out,
+                      float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
+  {
+    const int dblocks = (int)(D / kUDBlock), rblocks = (int)(cdiv(N, 128) * 128 / kUK);
+    if (std::max(1, std::min(rblocks / 8, kNumSMs / dblocks)) != 1)
+      return SDN_E_UNSUPPORTED;   // phase B would split the bank rows: the correction cannot be fused
+  }
+  for (int64_t q0 = 0; q0 < Q; q0 += kUQ) {
+    const int64_t qn = std::min<int64_t>(kUQ, Q - q0);
+    AccumEpi epi{};
+    epi.z = z + q0; epi.eps = eps; epi.scale = scale; epi.gate_thr = gate_thr; epi.flags = flags;
+    epi.x0 = x0_inout + q0 * D; epi.neg_out = neg_out ? neg_out + q0 * D : nullptr;
+    epi.denom_out = denom_out ? denom_out + q0 : nullptr; epi.gate_out = gate_out ? gate_out + q0 : nullptr;
+    epi.mean_out = mean_out; epi.inv_qd = 1.f / (float)(Q * D);
+    const int rc = umma_partial_64(planes, sqnorm, N, D, x0_inout + q0 * D, nullptr, qn, inv2s2, power, alpha,
+                                   num_out ? num_out + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws,
+                                   ws_bytes, st, &epi, q0 == 0 ? mean_out : nullptr);
     if (rc) return rc;
   }
   return SDN_OK;
@@ -506,7 +619,8 @@ int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, 
 
 static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                            const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
-                           float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                           float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, const AccumEpi* epi,
+                           float* zero_word) {
   const UmmaLayout L = umma_layout(N, D);
   if (!ws || ws_bytes < L.total) return SDN_E_WORKSPACE;
   if (!load_encode()) return SDN_E_DEVICE;
@@ -546,8 +660,14 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
 
   // query planes
   float* zpart = reinterpret_cast<float*>(w + L.off_z);
-  int pid = g_prof.begin("k_umma_xprep", st);
-  k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xq, (int)Q, D, xpl);
+  float* xsq_part = reinterpret_cast<float*>(w + L.off_q);
+  const int xsq_nparts = (int)cdiv(D, 1024);
+  int pid = g_prof.begin(xsq ? "k_umma_xprep" : "k_umma_qprep", st);
+  if (xsq) {
+    k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xq, (int)Q, D, xpl);
+  } else {
+    k_umma_qprep<<<dim3((unsigned)xsq_nparts, kUQ), 256, 0, st>>>(xq, (int)Q, D, xpl, xsq_part, zero_word);
+  }
   g_prof.end(pid, st);
   SDN_LAUNCHED();
 
@@ -563,8 +683,9 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
 
   // weights
   pid = g_prof.begin("k_umma_weights", st);
-  k_umma_weights<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(S_T, split_stride, L.ksplit, sqnorm, xsq, (int)N,
-                                                                      (int)Q, inv2s2, power, alpha, P, zpart, k_out);
+  k_umma_weights<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(S_T, split_stride, L.ksplit, sqnorm, xsq, xsq_part,
+                                                                      xsq_nparts, (int)N, (int)Q, inv2s2, power, alpha,
+                                                                      P, zpart, k_out);
   SDN_LAUNCHED();
   k_umma_zreduce<<<(unsigned)Q, 256, 0, st>>>(zpart, (int)(L.npad / kWRows), z);
   g_prof.end(pid, st);
@@ -574,10 +695,15 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   const int dblocks = (int)(D / kUDBlock);
   const int rblocks = (int)(L.npad / kUK);
   int nsplit = std::max(1, std::min(rblocks / 8, kNumSMs / dblocks));
-  if (nsplit > 1) SDN_CUDA_OK(cudaMemsetAsync(num, 0, sizeof(float) * Q * D, st));
+  AccumEpi e{};
+  if (epi) {
+    if (nsplit != 1) return SDN_E_UNSUPPORTED;
+    e = *epi;
+  }
+  if (nsplit > 1 && num) SDN_CUDA_OK(cudaMemsetAsync(num, 0, sizeof(float) * Q * D, st));
   pid = g_prof.begin("k_umma_accum", st);
   k_umma_accum<<<dim3(dblocks, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
-                                                                     nsplit, nsplit > 1 ? 1 : 0);
+                                                                     nsplit, nsplit > 1 ? 1 : 0, e);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;

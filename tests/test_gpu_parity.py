@@ -293,3 +293,30 @@ def test_errors_are_loud(nv):
     assert L.sdn_repel_partial(None, None, None, 1, 4, None, None, 1, 1.0, 1, 1.0, None, None, None, None, 0, 0, None) == -1
     assert L.sdn_bank_prepare(bank.flat.data_ptr(), 0, 256, bank.sqnorm.data_ptr(), None, None) == -2
     assert L.sdn_bank_prepare(bank.flat.data_ptr() + 4, 10, 256, bank.sqnorm.data_ptr(), None, None) == -3
+
+
+@pytest.mark.parametrize("Q,N", [(1, 515), (4, 131), (16, 515), (64, 384), (100, 300)])
+def test_fused_and_graphed_calls_match_three_call_sequence(nv, Q, N):
+    """sdn_conditioning_fused (2 / 5 launches) and the CUDA-graph replay give the same result as
+    query_prepare -> repel_partial -> epilogue_correct, call after call."""
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    bank4 = orc.synthetic_bank(N, 4, 64, 64)
+    bank = NegativeBank(bank4.cuda())
+    x_src = orc.synthetic_queries(bank4, Q, "near").cuda()
+    want = orc.conditioning_fast(x_src.cpu().numpy(), bank4.numpy(), scale=0.33, sigma=3.15)
+    ref = Projector(bank)
+    ref._few_launch[Q] = False                       # force the three-call sequence
+    xr = x_src.clone()
+    _, sr = ref.correct(xr, 3.15, 0.33, 1e-8, gate_threshold=1.0)
+    torch.cuda.synchronize()
+    assert rel(xr, want["x_0_hat"]) <= TOL
+    proj = Projector(bank)
+    x = torch.empty_like(x_src)
+    for it in range(4):                              # eager, capture+replay, replay, replay
+        x.copy_(x_src)
+        _, s = proj.correct_graphed(x, 3.15, 0.33, 1e-8, gate_threshold=1.0)
+        torch.cuda.synchronize()
+        assert rel(x, xr) <= 2e-5, it
+        assert rel(s.denom, sr.denom) <= 2e-5
+        assert (s.gate == sr.gate).all()
+        assert abs(float(s.mean) - float(sr.mean)) <= 1e-4 * abs(float(sr.mean)) + 1e-9
