@@ -83,7 +83,8 @@ int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes
     return SDN_E_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   g_prof.reset();
-  const int chosen = num_out ? pick_path(path, Q, N, D, planes) : SDN_PATH_GENERIC;
+  int chosen = pick_path(path, Q, N, D, planes);
+  if (!num_out && chosen == SDN_PATH_STREAM) chosen = SDN_PATH_GENERIC;   // z only: phase A kernels only
   switch (chosen) {
     case SDN_PATH_STREAM:
       if (!bank) return SDN_E_NULL;

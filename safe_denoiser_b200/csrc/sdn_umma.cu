@@ -583,8 +583,8 @@ int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, 
   for (int64_t q0 = 0; q0 < Q; q0 += kUQ) {
     const int64_t qn = std::min<int64_t>(kUQ, Q - q0);
     const int rc = umma_partial_64(planes, sqnorm, N, D, xq + q0 * D, xsq + q0, qn, inv2s2, power, alpha,
-                                   num + q0 * D, z + q0, k_out ? k_out + q0 * N : nullptr, ws, ws_bytes, st, nullptr,
-                                   nullptr);
+                                   num ? num + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws,
+                                   ws_bytes, st, nullptr, nullptr);
     if (rc) return rc;
   }
   return SDN_OK;
@@ -690,6 +690,8 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   k_umma_zreduce<<<(unsigned)Q, 256, 0, st>>>(zpart, (int)(L.npad / kWRows), z);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
+
+  if (!num && !epi) return SDN_OK;   // z only (empirical_beta): no phase B
 
   // phase B: one CTA per 128 d, bank rows split when that leaves SMs idle
   const int dblocks = (int)(D / kUDBlock);

@@ -320,3 +320,19 @@ def test_fused_and_graphed_calls_match_three_call_sequence(nv, Q, N):
         assert rel(s.denom, sr.denom) <= 2e-5
         assert (s.gate == sr.gate).all()
         assert abs(float(s.mean) - float(sr.mean)) <= 1e-4 * abs(float(sr.mean)) + 1e-9
+
+
+def test_empirical_beta_sd14_shape(tmp_path):
+    """threshold.py:351-384 at the real bank shape (N=515, 4x64x64): beta_j for every noisy row through the
+    tensor-core distance kernel (z only), quantiles against the oracle."""
+    bank4 = orc.synthetic_bank(515, 4, 64, 64)
+    g = torch.Generator().manual_seed(42)
+    noisy = {t: a * bank4 + (1 - a * a) ** 0.5 * torch.randn(bank4.shape, generator=g)
+             for t, a in ((801, 0.3), (401, 0.8), (1, 0.999))}
+    proc = _build("threshold", "kernel_fast", bank4.numpy(), tmp_path, scale=0.33, sigma=3.15, beta_threshold=1.0)
+    proc.noisy_proj_refs = {t: v.cuda() for t, v in noisy.items()}
+    for qt in (0.0, 0.5):
+        got = proc.empirical_beta(sigma=3.15, quantitle=qt)
+        want = orc.empirical_beta({t: v.numpy() for t, v in noisy.items()}, bank4.numpy(), sigma=3.15, quantile=qt)
+        for t in noisy:
+            assert abs(float(got[t]) / want[t] - 1) <= TOL, (qt, t, float(got[t]), want[t])
