@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--path", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 stream, 3 umma")
+    ap.add_argument("--path", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 stream, 3 tcgen05, 4 tcgen05 reading only the bf16 hi plane")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -145,7 +145,8 @@ def main():
     D = C * H * W
     base = {"metric": "repellency projections/sec", "unit": "projections/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16 bank planes (opt-in, outside the parity tolerance)" if args.path == 4 else "f32",
+            "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "Q": Q, "N": N, "latent": [C, H, W],
                        "sigma": wl["sigma"], "scale": wl["scale"], "semantics": wl["kind"],
                        "parallelism": f"N-sharded bank over {args.gpus} GPU(s), one NCCL all-reduce of [Q,D+1] fp32"
@@ -184,7 +185,7 @@ def main():
 
     bank_cpu = orc.synthetic_bank(N, C, H, W)
     lo, hi = shard_bounds(N, rank, world)
-    bank = NegativeBank(bank_cpu[lo:hi].to(dev), with_planes=(args.path in (0, 3)))
+    bank = NegativeBank(bank_cpu[lo:hi].to(dev), with_planes=(args.path in (0, 3, 4)))
     proj = Projector(bank, path=args.path, group=group)
     x_src = orc.synthetic_queries(bank_cpu, Q, "near").to(dev)
     x = x_src.clone()
@@ -244,7 +245,7 @@ def main():
     p0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     p1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     x.copy_(x_src)
-    if args.path in (0, 3) and Q > 8 and D % 128 == 0:
+    if args.path in (0, 3, 4) and Q > 8 and D % 128 == 0:
         bank.ensure_planes()
     kernel_ms = {}
     nv.profile_enable(True)
@@ -310,7 +311,7 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         n_local = hi - lo
         npad = (n_local + 127) // 128 * 128
-        bank_bytes = n_local * D * 4                      # fp32 bank == bf16 hi+lo planes: 4 B per element
+        bank_bytes = n_local * D * (2 if args.path == 4 else 4)   # fp32 bank == bf16 hi+lo planes: 4 B per element
         stage_bytes = bank_bytes + n_local * 4 + 2 * Q * D * 4   # one pass over the bank
         # algorithmic bytes of each kernel of the stage (what it must read + write once)
         kbytes = {

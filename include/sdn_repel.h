@@ -50,7 +50,9 @@ enum {
   SDN_PATH_AUTO = 0,
   SDN_PATH_GENERIC = 1,   /* CUDA-core two-phase kernels, any shape */
   SDN_PATH_STREAM = 2,    /* one-pass cluster kernel, GEMV-shaped (small Q) */
-  SDN_PATH_UMMA = 3       /* tcgen05 / TMEM / TMA two-phase kernels, batched Q */
+  SDN_PATH_UMMA = 3,      /* tcgen05 / TMEM / TMA two-phase kernels, batched Q */
+  SDN_PATH_UMMA_BF16 = 4  /* same kernels reading ONLY the bf16 hi plane of the bank: half the bytes per pass,
+                             outside the 1e-3 parity tolerance near a negative; explicit opt-in, never AUTO */
 };
 
 /* Epilogue flags (bit-or). */

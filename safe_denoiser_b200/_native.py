@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdn_repel.so")
 
-PATH_AUTO, PATH_GENERIC, PATH_STREAM, PATH_UMMA = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_STREAM, PATH_UMMA, PATH_UMMA_BF16 = 0, 1, 2, 3, 4
 EPI_GATE, EPI_RETURN_NEG = 1, 2
 
 _lib = None

@@ -67,7 +67,8 @@ size_t sdn_repel_workspace_bytes(int64_t Q, int64_t N, int64_t D, int32_t path) 
   if (Q <= 0 || N <= 0 || D <= 0) return 0;
   size_t need = generic_workspace_bytes(Q, N);
   if (path == SDN_PATH_AUTO || path == SDN_PATH_STREAM) need = std::max(need, stream_workspace_bytes(Q, N, D));
-  if (path == SDN_PATH_AUTO || path == SDN_PATH_UMMA) need = std::max(need, umma_workspace_bytes(Q, N, D));
+  if (path == SDN_PATH_AUTO || path == SDN_PATH_UMMA || path == SDN_PATH_UMMA_BF16)
+    need = std::max(need, umma_workspace_bytes(Q, N, D));
   return need;
 }
 
@@ -92,9 +93,10 @@ int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes
       return stream_partial(bank, sqnorm, N, D, xq, xsq, Q, inv_two_sigma_sq, dist_power, bank_alpha,
                             num_out, z_out, k_out, workspace, workspace_bytes, st);
     case SDN_PATH_UMMA:
+    case SDN_PATH_UMMA_BF16:
       if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
       return umma_partial(planes, sqnorm, N, D, xq, xsq, Q, inv_two_sigma_sq, dist_power, bank_alpha,
-                          num_out, z_out, k_out, workspace, workspace_bytes, st);
+                          num_out, z_out, k_out, workspace, workspace_bytes, st, chosen == SDN_PATH_UMMA_BF16);
     case SDN_PATH_GENERIC: break;
     default: return SDN_E_PARAM;
   }

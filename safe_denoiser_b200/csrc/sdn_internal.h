@@ -39,7 +39,8 @@ bool umma_supported(int64_t Q, int64_t N, int64_t D, const void* planes);
 size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D);
 int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                  const float* xsq, int64_t Q, float inv_two_sigma_sq, int power, float alpha,
-                 float* num, float* z, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                 float* num, float* z, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st,
+                 bool bf16_bank = false);
 
 int umma_conditioning(const void* planes, const float* sqnorm, int64_t N, int64_t D, float* x0_inout, int64_t Q,
                       float inv_two_sigma_sq, int power, float alpha, float eps, float scale, float gate_thr,

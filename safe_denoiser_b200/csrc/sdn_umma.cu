@@ -204,7 +204,7 @@ constexpr int kUChunk = 4;
 __global__ void __launch_bounds__(kUThreads, 1)
 k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
             const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int64_t split_stride,
-            int kblocks_total, int ksplit) {
+            int kblocks_total, int ksplit, int use_lo) {
   extern __shared__ unsigned char smem_raw[];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,11 +232,11 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const int s = i % kUStages;
         if (i >= kUStages) u_mbar_wait(&sm.empty[s], (uint32_t)(((i / kUStages) + 1) & 1));
         uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
-        u_mbar_expect_tx(&sm.full[s], kStageBytes);
+        u_mbar_expect_tx(&sm.full[s], use_lo ? kStageBytes : 2 * kTileBytes);
         const int kc = (kb0 + i) * kUK;
         u_tma_2d(st, &tm_x, kc, 0, &sm.full[s]);
         u_tma_2d(st + kTileBytes, &tm_hi, kc, row0, &sm.full[s]);
-        u_tma_2d(st + 2 * kTileBytes, &tm_lo, kc, row0, &sm.full[s]);
+        if (use_lo) u_tma_2d(st + 2 * kTileBytes, &tm_lo, kc, row0, &sm.full[s]);
       }
     }
   } else if (warp == 1) {
@@ -261,7 +261,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             const uint64_t bh = u_desc(base + kTileBytes + kk * 32, 16, 1024);
             const uint64_t bl = u_desc(base + 2 * kTileBytes + kk * 32, 16, 1024);
             u_mma(acc, a, bh, idesc, (i > c * kUChunk || kk > 0) ? 1u : 0u);
-            u_mma(acc, a, bl, idesc, 1u);
+            if (use_lo) u_mma(acc, a, bl, idesc, 1u);
           }
           u_commit(&sm.empty[s]);
         }
@@ -376,21 +376,24 @@ struct AccumEpi {
 __global__ void __launch_bounds__(kUThreads, 1)
 k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
              const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
-             int rblocks_total, int nsplit, int use_atomic, const AccumEpi epi) {
+             int rblocks_total, int nsplit, int use_atomic, int use_lo, const AccumEpi epi) {
   extern __shared__ unsigned char smem_raw[];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d0 = blockIdx.x * kUDBlock;
   const int rb0 = (int)((int64_t)blockIdx.y * rblocks_total / nsplit);
   const int rb1 = (int)((int64_t)(blockIdx.y + 1) * rblocks_total / nsplit);
   const int nrb = rb1 - rb0;
+  // persistent over d-blocks: this CTA owns blocks blockIdx.x, blockIdx.x + gridDim.x, ... and alternates
+  // between two TMEM accumulators so that the epilogue of one block overlaps the stream of the next
+  const int dblocks = (int)(D / kUDBlock);
+  const int ntasks = (dblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kUStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
-    u_mbar_init(&sm.acc_full[0], 1);
+    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) u_tmem_alloc(sm.tmem_base, kUStack);
+  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kUStack);
   u_fence_before();
   __syncthreads();
   u_fence_after();
@@ -399,11 +402,13 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   if (warp == 0) {
     if (lane == 0) {
       u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
-      for (int i = 0; i < nrb; ++i) {
-        const int s = i % kUStages;
-        if (i >= kUStages) u_mbar_wait(&sm.empty[s], (uint32_t)(((i / kUStages) + 1) & 1));
+      for (int it = 0; it < ntasks * nrb; ++it) {
+        const int t = it / nrb, i = it - t * nrb;
+        const int d0 = ((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock;
+        const int s = it % kUStages;
+        if (it >= kUStages) u_mbar_wait(&sm.empty[s], (uint32_t)(((it / kUStages) + 1) & 1));
         uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
-        u_mbar_expect_tx(&sm.full[s], kStageBytes);
+        u_mbar_expect_tx(&sm.full[s], use_lo ? kStageBytes : 2 * kTileBytes);
         const int rc = (rb0 + i) * kUK;                   // first bank row of this block
         // P tile: two boxes of [64 rows][64 stacked q] (hi parts, lo parts), 8 KiB apart
         u_tma_2d(st, &tm_p, 0, rc, &sm.full[s]);
@@ -411,39 +416,53 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart
         u_tma_2d(st + kTileBytes, &tm_hi, d0, rc, &sm.full[s]);
         u_tma_2d(st + kTileBytes + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
-        u_tma_2d(st + 2 * kTileBytes, &tm_lo, d0, rc, &sm.full[s]);
-        u_tma_2d(st + 2 * kTileBytes + 8192, &tm_lo, d0 + 64, rc, &sm.full[s]);
+        if (use_lo) {
+          u_tma_2d(st + 2 * kTileBytes, &tm_lo, d0, rc, &sm.full[s]);
+          u_tma_2d(st + 2 * kTileBytes + 8192, &tm_lo, d0 + 64, rc, &sm.full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t id_full = u_idesc(kUDBlock, kUStack, 1, 1);   // hi * [P_hi | P_lo]
       constexpr uint32_t id_half = u_idesc(kUDBlock, kUQ, 1, 1);       // lo * P_hi
-      for (int i = 0; i < nrb; ++i) {
-        const int s = i % kUStages;
-        u_mbar_wait(&sm.full[s], (uint32_t)((i / kUStages) & 1));
-        u_fence_after();
-        const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
-#pragma unroll
-        for (int kk = 0; kk < kUK / 16; ++kk) {
-          const uint64_t b = u_desc(base + kk * 2048, 8192, 1024);                    // P^T, MN-major
-          const uint64_t ah = u_desc(base + kTileBytes + kk * 2048, 8192, 1024);      // bank^T, MN-major
-          const uint64_t al = u_desc(base + 2 * kTileBytes + kk * 2048, 8192, 1024);
-          u_mma(tmem, ah, b, id_full, (i > 0 || kk > 0) ? 1u : 0u);
-          u_mma(tmem, al, b, id_half, 1u);
+      for (int t = 0; t < ntasks; ++t) {
+        const int buf = t & 1;
+        if (t >= 2) {
+          u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((t >> 1) + 1) & 1));
+          u_fence_after();
         }
-        u_commit(&sm.empty[s]);
+        const uint32_t acc = tmem + (uint32_t)(buf * kUStack);
+        for (int i = 0; i < nrb; ++i) {
+          const int it = t * nrb + i;
+          const int s = it % kUStages;
+          u_mbar_wait(&sm.full[s], (uint32_t)((it / kUStages) & 1));
+          u_fence_after();
+          const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < kUK / 16; ++kk) {
+            const uint64_t b = u_desc(base + kk * 2048, 8192, 1024);                    // P^T, MN-major
+            const uint64_t ah = u_desc(base + kTileBytes + kk * 2048, 8192, 1024);      // bank^T, MN-major
+            const uint64_t al = u_desc(base + 2 * kTileBytes + kk * 2048, 8192, 1024);
+            u_mma(acc, ah, b, id_full, (i > 0 || kk > 0) ? 1u : 0u);
+            if (use_lo) u_mma(acc, al, b, id_half, 1u);
+          }
+          u_commit(&sm.empty[s]);
+        }
+        u_commit(&sm.acc_full[buf]);
       }
-      u_commit(&sm.acc_full[0]);
     }
   } else {
     // epilogue: TMEM lane = d within the block, column = stacked query row
     const int lq = warp & 3;
-    u_mbar_wait(&sm.acc_full[0], 0);
-    u_fence_after();
-    const int64_t d = (int64_t)d0 + lq * 32 + lane;
-    const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);
     float msum = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < ntasks; ++t) {
+    const int buf = t & 1;
+    u_mbar_wait(&sm.acc_full[buf], (uint32_t)((t >> 1) & 1));
+    u_fence_after();
+    const int64_t d = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock + lq * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kUStack);
 #pragma unroll 1
     for (int c = 0; c < kUQ / 32; ++c) {
       float a[32], b[32];
@@ -487,6 +506,10 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         }
       }
     }
+    u_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
+    }   // tasks
     if (epi.z && epi.mean_out) {
       msum = warp_sum(msum);
       if (lane == 0) atomicAdd(epi.mean_out, msum * epi.inv_qd);
@@ -496,7 +519,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   __syncthreads();
   if (warp == 1) {
     u_fence_after();
-    u_tmem_dealloc(tmem, kUStack);
+    u_tmem_dealloc(tmem, 2 * kUStack);
   }
 }
 
@@ -531,8 +554,9 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
 int umma_ksplit(int64_t npad, int64_t D) {
   const int row_tiles = (int)(npad / kUBankTile);
   const int kblocks = (int)(D / kUK);
-  int ksplit = std::max(1, std::min(kblocks / 4, (kNumSMs + row_tiles / 2) / row_tiles));
-  return std::min(ksplit, 16);
+  // one task per SM if possible, at least 8 K-blocks per task (fill/drain), at most 64 partial buffers
+  int ksplit = std::max(1, std::min(kblocks / 8, kNumSMs / row_tiles));   // never a second, nearly empty wave
+  return std::min(ksplit, 64);
 }
 
 struct UmmaLayout {
@@ -572,19 +596,19 @@ size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D) {
 static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                            const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
                            float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, const AccumEpi* epi,
-                           float* zero_word);
+                           float* zero_word, bool bf16_bank);
 
 // More than 64 query rows: one two-phase pass over the bank per group of 64 (the TMEM accumulator of phase B
 // holds 128 d x 128 stacked query columns).
 int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                  const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
-                 float* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, bool bf16_bank) {
   if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
   for (int64_t q0 = 0; q0 < Q; q0 += kUQ) {
     const int64_t qn = std::min<int64_t>(kUQ, Q - q0);
     const int rc = umma_partial_64(planes, sqnorm, N, D, xq + q0 * D, xsq + q0, qn, inv2s2, power, alpha,
                                    num ? num + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws,
-                                   ws_bytes, st, nullptr, nullptr);
+                                   ws_bytes, st, nullptr, nullptr, bf16_bank);
     if (rc) return rc;
   }
   return SDN_OK;
@@ -611,7 +635,7 @@ int umma_conditioning(const void* planes, const float* sqnorm, int64_t N, int64_
     epi.mean_out = mean_out; epi.inv_qd = 1.f / (float)(Q * D);
     const int rc = umma_partial_64(planes, sqnorm, N, D, x0_inout + q0 * D, nullptr, qn, inv2s2, power, alpha,
                                    num_out ? num_out + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws,
-                                   ws_bytes, st, &epi, q0 == 0 ? mean_out : nullptr);
+                                   ws_bytes, st, &epi, q0 == 0 ? mean_out : nullptr, false);
     if (rc) return rc;
   }
   return SDN_OK;
@@ -620,7 +644,7 @@ int umma_conditioning(const void* planes, const float* sqnorm, int64_t N, int64_
 static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                            const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
                            float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, const AccumEpi* epi,
-                           float* zero_word) {
+                           float* zero_word, bool bf16_bank) {
   const UmmaLayout L = umma_layout(N, D);
   if (!ws || ws_bytes < L.total) return SDN_E_WORKSPACE;
   if (!load_encode()) return SDN_E_DEVICE;
@@ -677,7 +701,7 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   const int64_t split_stride = L.npad * kUStack;
   pid = g_prof.begin("k_umma_dots", st);
   k_umma_dots<<<dim3(row_tiles, L.ksplit), kUThreads, kUSmemBytes, st>>>(tm_x, tm_hiA, tm_loA, S_T, split_stride,
-                                                                        kblocks, L.ksplit);
+                                                                        kblocks, L.ksplit, bf16_bank ? 0 : 1);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
 
@@ -704,8 +728,9 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   }
   if (nsplit > 1 && num) SDN_CUDA_OK(cudaMemsetAsync(num, 0, sizeof(float) * Q * D, st));
   pid = g_prof.begin("k_umma_accum", st);
-  k_umma_accum<<<dim3(dblocks, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
-                                                                     nsplit, nsplit > 1 ? 1 : 0, e);
+  const int gridx = nsplit == 1 ? std::min(dblocks, kNumSMs) : dblocks;
+  k_umma_accum<<<dim3(gridx, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
+                                                                     nsplit, nsplit > 1 ? 1 : 0, bf16_bank ? 0 : 1, e);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;

@@ -173,7 +173,7 @@ class Projector:
         L = nv.lib()
         st = nv.current_stream()
         Q, xf = self._flat_query(x0)
-        if Q > 8 and self.path in (nv.PATH_AUTO, nv.PATH_UMMA) and self.bank.D % 128 == 0:
+        if Q > 8 and self.path in (nv.PATH_AUTO, nv.PATH_UMMA, nv.PATH_UMMA_BF16) and self.bank.D % 128 == 0:
             self.bank.ensure_planes()        # batched calls go to the tcgen05 kernels
         s = self._get(Q, normalize_channels > 0)
         mo = None

@@ -336,3 +336,16 @@ def test_empirical_beta_sd14_shape(tmp_path):
         want = orc.empirical_beta({t: v.numpy() for t, v in noisy.items()}, bank4.numpy(), sigma=3.15, quantile=qt)
         for t in noisy:
             assert abs(float(got[t]) / want[t] - 1) <= TOL, (qt, t, float(got[t]), want[t])
+
+
+def test_bf16_bank_mode_reports_its_own_error(nv):
+    """SDN_PATH_UMMA_BF16 (opt-in): half the bank bytes, looser than the parity tolerance near a negative.
+    Measured bound asserted here: x0' within 1e-3 for queries that are not within ~0.05*randn of a negative,
+    weights within 5e-2 in the near regime (documented in DESIGN.md)."""
+    bank = orc.synthetic_bank(600, 4, 64, 64)
+    for regime, tol_x0, tol_w in (("x0", 1e-3, 5e-3), ("far", 1e-3, 5e-3), ("near", 5e-3, 5e-2)):
+        x = orc.synthetic_queries(bank, 16, regime)
+        want = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.33, sigma=3.15)
+        got = run_projection(nv, bank, x, 3.15, 0.33, path=nv.PATH_UMMA_BF16)
+        assert rel(got["x0"], want["x_0_hat"]) <= tol_x0, regime
+        assert rel(got["weights"], want["weights"]) <= tol_w, regime
