@@ -331,6 +331,13 @@ def main():
             dom_bytes = kbytes.get(dom, stage_bytes)
         else:
             dom, dom_ms, dom_bytes = "sdn_repel_partial", part_avg_ms, stage_bytes
+        # DRAM bytes of that kernel from the committed `ncu --set full` capture of the same workload, if any
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            ent = json.load(open(tpath)).get(f"{args.workload}/{dom}")
+            if ent:
+                traffic, traffic_src = ent["bytes"], ent["source"]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         stage_achieved = stage_bytes / (part_avg_ms * 1e-3) / 1e9
         line = dict(base)
@@ -350,7 +357,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "projections/s", "h2d_bytes_per_step": Q * D * 4,
                     "d2h_bytes_per_step": Q * D * 4 + Q * 4, "steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": dom, "algorithmic_bytes": dom_bytes, "avg_ms": dom_ms,
                          "share_of_stage": dom_ms / part_avg_ms,
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
