@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--path", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 stream, 3 tcgen05, 4 tcgen05 reading only the bf16 hi plane")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sparse", action="store_true",
+                    help="let the accumulate pass skip bank-row blocks whose weights are below fp32 resolution "
+                         "(library default; off here so that the bench measures the dense worst case)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -176,6 +179,7 @@ def main():
     from oracle import repellency_oracle as orc   # synthetic inputs + cpu_baseline only
 
     nv.lib()   # raises if the CUDA library is missing: no fallback
+    nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, 1 if args.sparse else 0)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     group = None
@@ -345,6 +349,8 @@ def main():
                               l2="flushed between steps (256 MiB memset outside the per-step events)",
                               timing="sum of per-step CUDA-event intervals, max over ranks",
                               kernel_path=args.path,
+                              accumulate_pass="block-sparse (rows below fp32 resolution skipped)" if args.sparse
+                              else "dense (every bank row read; the library default would skip negligible rows)",
                               launch="one CUDA graph replay per step (kernels captured from the eager call)"
                               if use_graph else "eager launches",
                               e2e_call="sdn_conditioning_host (C ABI, pinned host buffers)" if world == 1

@@ -68,6 +68,14 @@ const char* sdn_error_string(int code);
 /* Number of kernels this library has launched since load (all entry points); bench.py reports it. */
 uint64_t sdn_launch_count(void);
 
+/* Library-wide options.
+ * SDN_OPT_SKIP_NEGLIGIBLE (default 1): the tcgen05 accumulate pass does not read blocks of 64 bank rows in which
+ *   every weight k_qi is below 1e-9 x the largest weight of its query (their total contribution is < N * 1e-9 of
+ *   the dominant term, below fp32 summation noise).  Exact to rounding, data dependent; 0 forces the dense pass
+ *   (bench.py's default, so that its numbers are the worst case). */
+enum { SDN_OPT_SKIP_NEGLIGIBLE = 1 };
+int sdn_set_option(int32_t key, int32_t value);
+
 /* Per-kernel timing of the LAST sdn_repel_partial call (CUDA events on its stream).  Off by default.
  * sdn_profile_read(i, ...) returns 1 and fills the i-th kernel's name and duration in ms (it synchronises on
  * that kernel's end event), 0 when i is out of range.  bench.py uses it for the roofline of the dominant kernel. */

@@ -21,6 +21,7 @@ SIGNATURES = {
     "sdn_abi_version": (C.c_int, []),
     "sdn_error_string": (C.c_char_p, [C.c_int]),
     "sdn_launch_count": (C.c_uint64, []),
+    "sdn_set_option": (C.c_int, [_i32, _i32]),
     "sdn_profile_enable": (None, [_i32]),
     "sdn_profile_read": (_i32, [_i32, C.c_char_p, _i32, C.POINTER(C.c_float)]),
     "sdn_bank_prepare": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
@@ -89,6 +90,13 @@ def ptr(t):
 def current_stream():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+OPT_SKIP_NEGLIGIBLE = 1
+
+
+def set_option(key, value):
+    check(lib().sdn_set_option(int(key), int(value)))
 
 
 def profile_enable(on=True):

@@ -47,6 +47,13 @@ const char* sdn_error_string(int code) {
   return "unknown error";
 }
 
+int sdn_set_option(int32_t key, int32_t value) {
+  switch (key) {
+    case SDN_OPT_SKIP_NEGLIGIBLE: g_skip_negligible.store(value != 0); return SDN_OK;
+    default: return SDN_E_PARAM;
+  }
+}
+
 void sdn_profile_enable(int32_t on) { g_prof.enabled = on != 0; g_prof.reset(); }
 
 int32_t sdn_profile_read(int32_t index, char* name_out, int32_t name_cap, float* ms_out) {

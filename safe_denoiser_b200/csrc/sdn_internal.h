@@ -34,6 +34,8 @@ int stream_conditioning(const float* bank, const float* sqnorm, int64_t N, int64
                         float* denom_out, int32_t* gate_out, float* mean_out, float* k_out, void* ws,
                         size_t ws_bytes, cudaStream_t st);
 
+extern std::atomic<bool> g_skip_negligible;   // SDN_OPT_SKIP_NEGLIGIBLE
+
 // ---- tcgen05 two-phase path for batched calls (sdn_umma.cu) ----
 bool umma_supported(int64_t Q, int64_t N, int64_t D, const void* planes);
 size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D);

@@ -346,25 +346,65 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
   zs[rsub][q] = k;
   __syncthreads();
   if (threadIdx.x < kUQ) {
-    float t = 0.f;
+    float t = 0.f, m = 0.f;
 #pragma unroll
-    for (int r = 0; r < kWRows; ++r) t += zs[r][threadIdx.x];
-    zpart[(int64_t)blockIdx.x * kUQ + threadIdx.x] = t;
+    for (int r = 0; r < kWRows; ++r) {
+      t += zs[r][threadIdx.x];
+      m = fmaxf(m, zs[r][threadIdx.x]);
+    }
+    zpart[(int64_t)blockIdx.x * kUStack + threadIdx.x] = t;          // [block][0..63]  sums
+    zpart[(int64_t)blockIdx.x * kUStack + kUQ + threadIdx.x] = m;    // [block][64..127] maxima
   }
 }
 
-// z[q] = sum_b zpart[b][q]; one block per query row.
+// z[q] = sum_b zpart[b][q], kmax[q] = max_b zpart[b][64+q]; one block per query row.
 __global__ void __launch_bounds__(256)
-k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__ z) {
+k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__ z, float* __restrict__ kmax) {
   __shared__ float red[33];
+  __shared__ float mx[8];
   const int q = blockIdx.x;
-  float t = 0.f;
-  for (int b = threadIdx.x; b < nblocks; b += 256) t += zpart[(int64_t)b * kUQ + q];
+  float t = 0.f, m = 0.f;
+  for (int b = threadIdx.x; b < nblocks; b += 256) {
+    t += zpart[(int64_t)b * kUStack + q];
+    m = fmaxf(m, zpart[(int64_t)b * kUStack + kUQ + q]);
+  }
   t = block_sum(t, red);
-  if (threadIdx.x == 0) z[q] = t;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) mx[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    z[q] = t;
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, mx[w]);
+    kmax[q] = m;
+  }
+}
+
+// Block-sparse phase B.  With a small sigma the weights of a query span many orders of magnitude; a block of 64
+// bank rows in which EVERY weight is below kSkipRel times its query's largest weight contributes less than
+// N * kSkipRel (3e-6 at N = 3000) relative to the dominant term -- below the fp32 summation noise -- and phase B
+// does not read it.  flags[rb] = 1 when row block rb holds at least one weight above that bound.
+constexpr float kSkipRel = 1e-9f;
+
+__global__ void __launch_bounds__(256)
+k_umma_rowflags(const __nv_bfloat16* __restrict__ P, const float* __restrict__ kmax, int Q, int* __restrict__ flags) {
+  const int q = threadIdx.x & (kUQ - 1), rsub = threadIdx.x >> 6;
+  const float bound = (q < Q) ? kSkipRel * kmax[q] : INFINITY;
+  const __nv_bfloat16* p = P + (int64_t)blockIdx.x * kUK * kUStack + q;
+  int hit = 0;
+#pragma unroll 4
+  for (int u = 0; u < kUK / 4; ++u) {
+    const float v = __bfloat162float(p[(int64_t)(rsub + 4 * u) * kUStack]);
+    hit |= (v > 0.f && v >= bound) ? 1 : 0;
+  }
+  hit = __syncthreads_or(hit);
+  if (threadIdx.x == 0) flags[blockIdx.x] = hit ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------ phase B
+constexpr int kMaxActive = 4096;   // row blocks a CTA can index in its active list (N <= 262144 per split)
+
 // Optional correction fused into phase B's epilogue (one GPU, no bank-row split): x0 -= scale * num / (z + eps).
 struct AccumEpi {
   const float* z;       // null: no fused correction
@@ -376,8 +416,11 @@ struct AccumEpi {
 __global__ void __launch_bounds__(kUThreads, 1)
 k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
              const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
-             int rblocks_total, int nsplit, int use_atomic, int use_lo, const AccumEpi epi) {
+             int rblocks_total, int nsplit, int use_atomic, int use_lo, const int* __restrict__ rowflags,
+             const AccumEpi epi) {
   extern __shared__ unsigned char smem_raw[];
+  __shared__ uint16_t act[kMaxActive];
+  __shared__ int nact_s;
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb0 = (int)((int64_t)blockIdx.y * rblocks_total / nsplit);
@@ -394,16 +437,35 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kUStack);
+  if (warp == 0) {
+    // compact the list of row blocks that hold a non-negligible weight (dense when no flags are given)
+    int cnt = 0;
+    if (rowflags) {
+      for (int base = 0; base < nrb; base += 32) {
+        const int i = base + lane;
+        const int f = (i < nrb) ? rowflags[rb0 + i] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, f != 0);
+        if (f) act[cnt + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
+        cnt += __popc(m);
+      }
+    } else {
+      cnt = nrb;
+    }
+    if (lane == 0) nact_s = cnt;
+  }
   u_fence_before();
   __syncthreads();
   u_fence_after();
   const uint32_t tmem = *sm.tmem_base;
+  const int nact = nact_s;
+  const bool dense = rowflags == nullptr;
 
   if (warp == 0) {
     if (lane == 0) {
       u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
-      for (int it = 0; it < ntasks * nrb; ++it) {
-        const int t = it / nrb, i = it - t * nrb;
+      for (int it = 0; it < ntasks * nact; ++it) {
+        const int t = it / nact, j = it - t * nact;
+        const int i = dense ? j : (int)act[j];
         const int d0 = ((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock;
         const int s = it % kUStages;
         if (it >= kUStages) u_mbar_wait(&sm.empty[s], (uint32_t)(((it / kUStages) + 1) & 1));
@@ -426,15 +488,15 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     if (lane == 0) {
       constexpr uint32_t id_full = u_idesc(kUDBlock, kUStack, 1, 1);   // hi * [P_hi | P_lo]
       constexpr uint32_t id_half = u_idesc(kUDBlock, kUQ, 1, 1);       // lo * P_hi
-      for (int t = 0; t < ntasks; ++t) {
+      for (int t = 0; t < ntasks && nact > 0; ++t) {
         const int buf = t & 1;
         if (t >= 2) {
           u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((t >> 1) + 1) & 1));
           u_fence_after();
         }
         const uint32_t acc = tmem + (uint32_t)(buf * kUStack);
-        for (int i = 0; i < nrb; ++i) {
-          const int it = t * nrb + i;
+        for (int i = 0; i < nact; ++i) {
+          const int it = t * nact + i;
           const int s = it % kUStages;
           u_mbar_wait(&sm.full[s], (uint32_t)((it / kUStages) & 1));
           u_fence_after();
@@ -459,15 +521,22 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 #pragma unroll 1
     for (int t = 0; t < ntasks; ++t) {
     const int buf = t & 1;
-    u_mbar_wait(&sm.acc_full[buf], (uint32_t)((t >> 1) & 1));
-    u_fence_after();
+    if (nact > 0) {
+      u_mbar_wait(&sm.acc_full[buf], (uint32_t)((t >> 1) & 1));
+      u_fence_after();
+    }
     const int64_t d = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock + lq * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kUStack);
 #pragma unroll 1
     for (int c = 0; c < kUQ / 32; ++c) {
       float a[32], b[32];
-      u_tmem_ld32(tl + (uint32_t)(c * 32), a);            // hi*P_hi + lo*P_hi, queries [32c, 32c+32)
-      u_tmem_ld32(tl + (uint32_t)(kUQ + c * 32), b);      // hi*P_lo
+      if (nact > 0) {
+        u_tmem_ld32(tl + (uint32_t)(c * 32), a);            // hi*P_hi + lo*P_hi, queries [32c, 32c+32)
+        u_tmem_ld32(tl + (uint32_t)(kUQ + c * 32), b);      // hi*P_lo
+      } else {                                              // no row block of this split matters: the sum is zero
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = b[j] = 0.f;
+      }
       if (epi.z) {
         // all loads of the chunk first: the stores below may alias them as far as the compiler knows, and one
         // load -> store round trip per query row costs ~25 us per launch
@@ -508,7 +577,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     }
     u_fence_before();
     __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
+    if (lane == 0 && nact > 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
     }   // tasks
     if (epi.z && epi.mean_out) {
       msum = warp_sum(msum);
@@ -524,6 +594,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------ host side
+std::atomic<bool> g_skip_negligible{true};
+
 namespace {
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 std::once_flag g_encode_once;
@@ -562,7 +634,7 @@ int umma_ksplit(int64_t npad, int64_t D) {
 struct UmmaLayout {
   int64_t npad;        // bank rows padded to 128
   int ksplit;
-  size_t off_x, off_s, off_p, off_z, off_q, total;
+  size_t off_x, off_s, off_p, off_z, off_f, off_q, total;
 };
 UmmaLayout umma_layout(int64_t N, int64_t D) {
   UmmaLayout L;
@@ -575,7 +647,9 @@ UmmaLayout umma_layout(int64_t N, int64_t D) {
   o = (o + 255) / 256 * 256;
   L.off_p = o; o += (size_t)kUStack * L.npad * 2;            // P planes
   o = (o + 255) / 256 * 256;
-  L.off_z = o; o += (size_t)(L.npad / kWRows) * kUQ * 4 + 256;   // per-block z partials + completion counter
+  L.off_z = o; o += (size_t)(L.npad / kWRows) * kUStack * 4 + 256;   // per-block z sums | maxima
+  o = (o + 255) / 256 * 256;
+  L.off_f = o; o += (size_t)(L.npad / kUK) * 4 + kUQ * 4 + 256;      // row-block flags + kmax[64]
   o = (o + 255) / 256 * 256;
   L.off_q = o; o += (size_t)cdiv(D, 1024) * kUQ * 4;          // ||x||^2 partials of the fused query prepare
   L.total = (o + 255) / 256 * 256;
@@ -711,9 +785,16 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
                                                                       xsq_nparts, (int)N, (int)Q, inv2s2, power, alpha,
                                                                       P, zpart, k_out);
   SDN_LAUNCHED();
-  k_umma_zreduce<<<(unsigned)Q, 256, 0, st>>>(zpart, (int)(L.npad / kWRows), z);
-  g_prof.end(pid, st);
+  int* rowflags = reinterpret_cast<int*>(w + L.off_f);
+  float* kmax = reinterpret_cast<float*>(w + L.off_f + (size_t)(L.npad / kUK) * 4);
+  k_umma_zreduce<<<(unsigned)Q, 256, 0, st>>>(zpart, (int)(L.npad / kWRows), z, kmax);
   SDN_LAUNCHED();
+  const bool sparse = g_skip_negligible.load(std::memory_order_relaxed) && (L.npad / kUK) <= kMaxActive;
+  if (sparse && (num || epi)) {
+    k_umma_rowflags<<<(unsigned)(L.npad / kUK), 256, 0, st>>>(P, kmax, (int)Q, rowflags);
+    SDN_LAUNCHED();
+  }
+  g_prof.end(pid, st);
 
   if (!num && !epi) return SDN_OK;   // z only (empirical_beta): no phase B
 
@@ -730,7 +811,8 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   pid = g_prof.begin("k_umma_accum", st);
   const int gridx = nsplit == 1 ? std::min(dblocks, kNumSMs) : dblocks;
   k_umma_accum<<<dim3(gridx, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
-                                                                     nsplit, nsplit > 1 ? 1 : 0, bf16_bank ? 0 : 1, e);
+                                                                     nsplit, nsplit > 1 ? 1 : 0, bf16_bank ? 0 : 1,
+                                                                     sparse ? rowflags : nullptr, e);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;

@@ -349,3 +349,21 @@ def test_bf16_bank_mode_reports_its_own_error(nv):
         got = run_projection(nv, bank, x, 3.15, 0.33, path=nv.PATH_UMMA_BF16)
         assert rel(got["x0"], want["x_0_hat"]) <= tol_x0, regime
         assert rel(got["weights"], want["weights"]) <= tol_w, regime
+
+
+@pytest.mark.parametrize("regime,sigma", [("near", 1.0), ("mid", 1.0), ("x0", 3.15), ("far", 13.15)])
+def test_block_sparse_accumulate_equals_dense(nv, regime, sigma):
+    """SDN_OPT_SKIP_NEGLIGIBLE: skipping row blocks whose weights are < 1e-9 of the query's largest weight must
+    not change the result beyond fp32 summation noise, in peaked (sigma = 1) and flat (sigma = 13) regimes."""
+    bank = orc.synthetic_bank(1000, 4, 64, 64)
+    x = orc.synthetic_queries(bank, 48, regime)
+    want = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.33, sigma=sigma)
+    out = {}
+    for on in (1, 0):
+        nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, on)
+        out[on] = run_projection(nv, bank, x, sigma, 0.33, path=nv.PATH_UMMA)
+        assert rel(out[on]["x0"], want["x_0_hat"]) <= TOL
+        assert rel(out[on]["weights"], want["weights"]) <= TOL
+    nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, 1)
+    assert rel(out[1]["num"], out[0]["num"]) <= 1e-5
+    assert rel(out[1]["denom"], out[0]["denom"]) == 0.0
