@@ -304,6 +304,24 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   }
 }
 
+constexpr int kListCap = 32;     // significant rows per query the listed accumulate handles
+
+struct SigLists {
+  int* flags;        // [Npad/64]      row block holds a significant weight
+  int* count;        // [64]           significant rows per query (may exceed kListCap)
+  int* dense;        // [1]            set by k_umma_zreduce when some query's weights are flat (z / kmax > cap):
+                     //                its list must overflow, so nobody builds lists or flags and phase B is dense
+  int* rows;         // [64][kListCap] their bank row indices (unsorted, first kListCap arrivals)
+  float* ks;         // [64][kListCap] their weights
+};
+
+// zeroes the lists (launched as part of k_umma_weights' grid: block 0 does it before anyone appends)
+__device__ __forceinline__ void siglist_clear(const SigLists& L, int nflags) {
+  for (int i = threadIdx.x; i < nflags; i += blockDim.x) L.flags[i] = 0;
+  if (threadIdx.x < kUQ) L.count[threadIdx.x] = 0;
+  if (threadIdx.x == 0) *L.dense = 0;
+}
+
 // ------------------------------------------------------------------------------------------ weights
 // One thread per (bank row, query row): sum the K-split partials, k = exp(-dist / 2 sigma^2), write the weight
 // planes P [Npad][128] bf16 (stacked query index contiguous: hi parts in columns [0,64), lo parts in [64,128)),
@@ -314,8 +332,9 @@ __global__ void __launch_bounds__(kWRows * kUQ)
 k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, const float* __restrict__ sqnorm,
                const float* __restrict__ xsq, const float* __restrict__ xsq_part, int xsq_nparts, int N, int Q,
                float inv2s2, int power, float alpha, __nv_bfloat16* __restrict__ P, float* __restrict__ zpart,
-               float* __restrict__ k_out) {
+               float* __restrict__ k_out, SigLists lists, int nflags) {
   __shared__ float zs[kWRows][kUQ];
+  if (blockIdx.x == 0 && lists.flags) siglist_clear(lists, nflags);
   const int q = threadIdx.x & (kUQ - 1);
   const int rsub = threadIdx.x >> 6;
   const int i = blockIdx.x * kWRows + rsub;
@@ -359,7 +378,8 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
 
 // z[q] = sum_b zpart[b][q], kmax[q] = max_b zpart[b][64+q]; one block per query row.
 __global__ void __launch_bounds__(256)
-k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__ z, float* __restrict__ kmax) {
+k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__ z, float* __restrict__ kmax,
+               int* __restrict__ dense_flag) {
   __shared__ float red[33];
   __shared__ float mx[8];
   const int q = blockIdx.x;
@@ -378,6 +398,9 @@ k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__
 #pragma unroll
     for (int w = 1; w < 8; ++w) m = fmaxf(m, mx[w]);
     kmax[q] = m;
+    // sum_i k_i / kmax <= (#rows with k_i >= tau kmax) + N tau: more than kListCap "effective rows" means the
+    // query's significant-row list must overflow
+    if (dense_flag && t > (float)kListCap * m) atomicOr(dense_flag, 1);
   }
 }
 
@@ -387,19 +410,114 @@ k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__
 // does not read it.  flags[rb] = 1 when row block rb holds at least one weight above that bound.
 constexpr float kSkipRel = 1e-9f;
 
-__global__ void __launch_bounds__(256)
-k_umma_rowflags(const __nv_bfloat16* __restrict__ P, const float* __restrict__ kmax, int Q, int* __restrict__ flags) {
+// One thread per (bank row, query row): mark row blocks and append (row, k) to the query's list when the weight is
+// significant.  grid = Npad / 4, block = 256.
+__global__ void __launch_bounds__(kWRows * kUQ)
+k_umma_siglist(const __nv_bfloat16* __restrict__ P, const float* __restrict__ kmax, int N, int Q, SigLists L) {
+  __shared__ int sg[kWRows][kUQ];
+  if (__ldg(L.dense)) return;                          // flat regime: dense phase B, nothing to build
   const int q = threadIdx.x & (kUQ - 1), rsub = threadIdx.x >> 6;
-  const float bound = (q < Q) ? kSkipRel * kmax[q] : INFINITY;
-  const __nv_bfloat16* p = P + (int64_t)blockIdx.x * kUK * kUStack + q;
-  int hit = 0;
-#pragma unroll 4
-  for (int u = 0; u < kUK / 4; ++u) {
-    const float v = __bfloat162float(p[(int64_t)(rsub + 4 * u) * kUStack]);
-    hit |= (v > 0.f && v >= bound) ? 1 : 0;
+  const int i = blockIdx.x * kWRows + rsub;
+  float k = 0.f;
+  bool sig = false;
+  if (i < N && q < Q) {
+    k = __bfloat162float(P[(int64_t)i * kUStack + q]) + __bfloat162float(P[(int64_t)i * kUStack + kUQ + q]);
+    sig = k > 0.f && k >= kSkipRel * kmax[q];
   }
-  hit = __syncthreads_or(hit);
-  if (threadIdx.x == 0) flags[blockIdx.x] = hit ? 1 : 0;
+  sg[rsub][q] = sig ? 1 : 0;
+  const int any = __syncthreads_or(sig ? 1 : 0);
+  if (any && threadIdx.x == 0) L.flags[(blockIdx.x * kWRows) / kUK] = 1;   // kWRows divides 64: one block, one flag
+  if (!sig) return;
+  // A query whose weights are significant on every row of this block is in a flat regime: its list would
+  // overflow anyway, so mark it overflowed with a plain store instead of hammering its counter; later threads
+  // see the mark and stop too.  Peaked regimes (the case the lists exist for) add a handful of entries.
+  if (sg[0][q] + sg[1][q] + sg[2][q] + sg[3][q] == kWRows) {
+    if (rsub == 0 && *reinterpret_cast<volatile int*>(L.count + q) <= kListCap)
+      *reinterpret_cast<volatile int*>(L.count + q) = kListCap + (1 << 20);
+    return;
+  }
+  if (*reinterpret_cast<volatile int*>(L.count + q) <= kListCap) {
+    const int pos = atomicAdd(L.count + q, 1);
+    if (pos < kListCap) {
+      L.rows[q * kListCap + pos] = i;
+      L.ks[q * kListCap + pos] = k;
+    }
+  }
+}
+
+// Block-cooperative (every thread of the block must call it): true when every query has at most kListCap
+// significant rows.  One parallel load per query row -- a serial loop of 64 dependent L2 loads costs ~25 us.
+__device__ __forceinline__ bool siglist_all_short(const int* count, int Q) {
+  bool ok = true;
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) ok = ok && (__ldcg(count + q) <= kListCap);
+  return __syncthreads_and(ok ? 1 : 0) != 0;
+}
+
+// Listed accumulate: when every query has at most kListCap significant bank rows (peaked weights: small sigma),
+// num[q] = sum over that query's list of k * (hi + lo)[row] on the CUDA cores -- a few MB instead of a pass over
+// the bank.  grid (D / 1024, Q), block 256, thread = 4 consecutive d.  Exits at once when a list overflowed
+// (k_umma_accum then does the block-sparse tensor-core pass).
+struct AccumEpi;
+__global__ void __launch_bounds__(256)
+k_umma_listed_accum(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t D, int Q,
+                    SigLists L, float* __restrict__ num, const float* z, float eps, float scale, float gate_thr,
+                    int flags, float* x0, float* neg_out, float* denom_out, int32_t* gate_out, float* mean_out,
+                    float inv_qd) {
+  __shared__ int srow[kListCap];
+  __shared__ float sk[kListCap];
+  __shared__ float red[33];
+  if (__ldg(L.dense) || !siglist_all_short(L.count, Q)) return;
+  const int q = blockIdx.y;
+  const int n = L.count[q];
+  // sort the list by row index so that the fp32 summation order does not depend on atomic arrival order
+  if (threadIdx.x < n) {
+    const int r = L.rows[q * kListCap + threadIdx.x];
+    int rank = 0;
+    for (int e = 0; e < n; ++e) rank += (L.rows[q * kListCap + e] < r) ? 1 : 0;
+    srow[rank] = r;
+    sk[rank] = L.ks[q * kListCap + threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t d = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  float msum = 0.f;
+  if (d < D) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < n; ++e) {
+      const int64_t o = (int64_t)srow[e] * D + d;
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + o));
+      const uint2 l = lo ? __ldg(reinterpret_cast<const uint2*>(lo + o)) : make_uint2(0u, 0u);   // bf16 zero bits
+      const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+      const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
+      const float k = sk[e];
+      acc.x = fmaf(k, __bfloat162float(hb[0]) + __bfloat162float(lb[0]), acc.x);
+      acc.y = fmaf(k, __bfloat162float(hb[1]) + __bfloat162float(lb[1]), acc.y);
+      acc.z = fmaf(k, __bfloat162float(hb[2]) + __bfloat162float(lb[2]), acc.z);
+      acc.w = fmaf(k, __bfloat162float(hb[3]) + __bfloat162float(lb[3]), acc.w);
+    }
+    const int64_t o = (int64_t)q * D + d;
+    if (num) *reinterpret_cast<float4*>(num + o) = acc;
+    if (z) {
+      const float denom = z[q] + eps;
+      const float4 nn = make_float4(acc.x / denom, acc.y / denom, acc.z / denom, acc.w / denom);
+      if (neg_out) *reinterpret_cast<float4*>(neg_out + o) = nn;
+      if (x0) {
+        float4 x = *reinterpret_cast<const float4*>(x0 + o);
+        x.x = fmaf(-scale, nn.x, x.x); x.y = fmaf(-scale, nn.y, x.y);
+        x.z = fmaf(-scale, nn.z, x.z); x.w = fmaf(-scale, nn.w, x.w);
+        *reinterpret_cast<float4*>(x0 + o) = x;
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (denom_out) denom_out[q] = denom;
+        if (gate_out) gate_out[q] = (!(flags & SDN_EPI_GATE) || denom > gate_thr) ? 1 : 0;
+      }
+      msum = fminf(fmaxf(nn.x, -1e10f), 1e10f) + fminf(fmaxf(nn.y, -1e10f), 1e10f) +
+             fminf(fmaxf(nn.z, -1e10f), 1e10f) + fminf(fmaxf(nn.w, -1e10f), 1e10f);
+    }
+  }
+  if (z && mean_out) {
+    msum = block_sum(msum, red);
+    if (threadIdx.x == 0) atomicAdd(mean_out, msum * inv_qd);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ phase B
@@ -416,8 +534,13 @@ struct AccumEpi {
 __global__ void __launch_bounds__(kUThreads, 1)
 k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
              const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
-             int rblocks_total, int nsplit, int use_atomic, int use_lo, const int* __restrict__ rowflags,
-             const AccumEpi epi) {
+             int rblocks_total, int nsplit, int use_atomic, int use_lo, const int* rowflags,
+             const int* __restrict__ list_count, const int* __restrict__ dense_flag, const AccumEpi epi) {
+  if (dense_flag && __ldg(dense_flag)) {
+    rowflags = nullptr;                                          // flat regime: no flags were built
+  } else if (list_count && siglist_all_short(list_count, Q)) {
+    return;                                                      // k_umma_listed_accum produced the result
+  }
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint16_t act[kMaxActive];
   __shared__ int nact_s;
@@ -649,7 +772,8 @@ UmmaLayout umma_layout(int64_t N, int64_t D) {
   o = (o + 255) / 256 * 256;
   L.off_z = o; o += (size_t)(L.npad / kWRows) * kUStack * 4 + 256;   // per-block z sums | maxima
   o = (o + 255) / 256 * 256;
-  L.off_f = o; o += (size_t)(L.npad / kUK) * 4 + kUQ * 4 + 256;      // row-block flags + kmax[64]
+  L.off_f = o; o += (size_t)(L.npad / kUK) * 4 + kUQ * 4 + kUQ * 4 + 16 + (size_t)kUQ * kListCap * 8 + 256;
+                                                       // row-block flags | kmax[64] | count[64] | rows | ks
   o = (o + 255) / 256 * 256;
   L.off_q = o; o += (size_t)cdiv(D, 1024) * kUQ * 4;          // ||x||^2 partials of the fused query prepare
   L.total = (o + 255) / 256 * 256;
@@ -780,22 +904,33 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   SDN_LAUNCHED();
 
   // weights
+  SigLists lists_w{};
+  if (g_skip_negligible.load(std::memory_order_relaxed) && (L.npad / kUK) <= kMaxActive && (num || epi)) {
+    lists_w.flags = reinterpret_cast<int*>(w + L.off_f);
+    lists_w.count = reinterpret_cast<int*>(reinterpret_cast<float*>(lists_w.flags + L.npad / kUK) + kUQ);
+    lists_w.dense = lists_w.count + kUQ;
+  }
   pid = g_prof.begin("k_umma_weights", st);
   k_umma_weights<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(S_T, split_stride, L.ksplit, sqnorm, xsq, xsq_part,
                                                                       xsq_nparts, (int)N, (int)Q, inv2s2, power, alpha,
-                                                                      P, zpart, k_out);
+                                                                      P, zpart, k_out, lists_w, (int)(L.npad / kUK));
   SDN_LAUNCHED();
-  int* rowflags = reinterpret_cast<int*>(w + L.off_f);
-  float* kmax = reinterpret_cast<float*>(w + L.off_f + (size_t)(L.npad / kUK) * 4);
-  k_umma_zreduce<<<(unsigned)Q, 256, 0, st>>>(zpart, (int)(L.npad / kWRows), z, kmax);
+  const int nflags = (int)(L.npad / kUK);
+  SigLists lists{};
+  lists.flags = reinterpret_cast<int*>(w + L.off_f);
+  float* kmax = reinterpret_cast<float*>(lists.flags + nflags);
+  lists.count = reinterpret_cast<int*>(kmax + kUQ);
+  lists.dense = lists.count + kUQ;
+  lists.rows = lists.dense + 4;
+  lists.ks = reinterpret_cast<float*>(lists.rows + kUQ * kListCap);
+  k_umma_zreduce<<<(unsigned)Q, 256, 0, st>>>(zpart, (int)(L.npad / kWRows), z, kmax, lists_w.flags ? lists.dense : nullptr);
   SDN_LAUNCHED();
-  const bool sparse = g_skip_negligible.load(std::memory_order_relaxed) && (L.npad / kUK) <= kMaxActive;
-  if (sparse && (num || epi)) {
-    k_umma_rowflags<<<(unsigned)(L.npad / kUK), 256, 0, st>>>(P, kmax, (int)Q, rowflags);
+  const bool sparse = g_skip_negligible.load(std::memory_order_relaxed) && nflags <= kMaxActive && (num || epi);
+  if (sparse) {
+    k_umma_siglist<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(P, kmax, (int)N, (int)Q, lists);
     SDN_LAUNCHED();
   }
   g_prof.end(pid, st);
-
   if (!num && !epi) return SDN_OK;   // z only (empirical_beta): no phase B
 
   // phase B: one CTA per 128 d, bank rows split when that leaves SMs idle
@@ -808,11 +943,21 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
     e = *epi;
   }
   if (nsplit > 1 && num) SDN_CUDA_OK(cudaMemsetAsync(num, 0, sizeof(float) * Q * D, st));
+  if (sparse) {
+    pid = g_prof.begin("k_umma_listed_accum", st);
+    k_umma_listed_accum<<<dim3((unsigned)cdiv(D, 1024), (unsigned)Q), 256, 0, st>>>(
+        hi, bf16_bank ? nullptr : lo, D, (int)Q, lists, num, epi ? e.z : nullptr, e.eps, e.scale, e.gate_thr, e.flags, e.x0,
+        e.neg_out, e.denom_out, e.gate_out, e.mean_out, e.inv_qd);
+    g_prof.end(pid, st);
+    SDN_LAUNCHED();
+  }
   pid = g_prof.begin("k_umma_accum", st);
   const int gridx = nsplit == 1 ? std::min(dblocks, kNumSMs) : dblocks;
   k_umma_accum<<<dim3(gridx, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
                                                                      nsplit, nsplit > 1 ? 1 : 0, bf16_bank ? 0 : 1,
-                                                                     sparse ? rowflags : nullptr, e);
+                                                                     sparse ? lists.flags : nullptr,
+                                                                     sparse ? lists.count : nullptr,
+                                                                     sparse ? lists.dense : nullptr, e);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;

@@ -367,3 +367,25 @@ def test_block_sparse_accumulate_equals_dense(nv, regime, sigma):
     nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, 1)
     assert rel(out[1]["num"], out[0]["num"]) <= 1e-5
     assert rel(out[1]["denom"], out[0]["denom"]) == 0.0
+
+
+def test_block_sparse_list_overflow_falls_back_to_tensor_core_pass(nv):
+    """Peaked weights (z / kmax ~ 1) but MORE than 32 rows above the 1e-9 significance bound: the per-query lists
+    overflow, the listed kernel must step aside and the block-sparse tcgen05 pass must produce the result."""
+    g = torch.Generator().manual_seed(3)
+    centres = torch.randn(4, 4, 64, 64, generator=g)
+    bank = torch.cat([centres] + [c[None] + 0.3 * torch.randn(70, 4, 64, 64, generator=g) for c in centres]
+                     + [5.0 + torch.randn(356, 4, 64, 64, generator=g)])   # 4 centres + 280 clustered + 356 far rows
+    perm = torch.randperm(bank.shape[0], generator=g)
+    bank = bank[perm].contiguous()
+    x = torch.stack([centres[i % 4] + 0.02 * torch.randn(4, 64, 64, generator=g) for i in range(24)])
+    want = orc.closed_form(x.numpy(), bank.numpy(), sigma=1.0)
+    nsig = (want["k"] >= 1e-9 * want["k"].max(1, keepdims=True)).sum(1)
+    assert nsig.min() > 32 and (want["Z"] / want["k"].max(1)).max() < 32      # the case this test is about
+    ref = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.5, sigma=1.0)
+    for on in (1, 0):
+        nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, on)
+        got = run_projection(nv, bank, x, 1.0, 0.5, path=nv.PATH_UMMA)
+        assert rel(got["x0"], ref["x_0_hat"]) <= TOL, on
+        assert rel(got["weights"], ref["weights"]) <= TOL, on
+    nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, 1)
