@@ -521,6 +521,7 @@ k_umma_listed_accum(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* _
 }
 
 // ------------------------------------------------------------------------------------------ phase B
+constexpr int kBChunk = 64;        // row blocks per TMEM accumulation chain in phase B (512 MMAs)
 constexpr int kMaxActive = 4096;   // row blocks a CTA can index in its active list (N <= 262144 per split)
 
 // Optional correction fused into phase B's epilogue (one GPU, no bank-row split): x0 -= scale * num / (z + eps).
@@ -531,6 +532,7 @@ struct AccumEpi {
 };
 
 // grid (D / 128, n splits).  num[q][d] (+)= sum_i P[q][i] * (hi+lo)[i][d] over this split's bank rows.
+template <bool CHUNKED>
 __global__ void __launch_bounds__(kUThreads, 1)
 k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
              const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
@@ -582,6 +584,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   const uint32_t tmem = *sm.tmem_base;
   const int nact = nact_s;
   const bool dense = rowflags == nullptr;
+  const int nchunks = max(1, (nact + kBChunk - 1) / kBChunk);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -611,6 +614,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     if (lane == 0) {
       constexpr uint32_t id_full = u_idesc(kUDBlock, kUStack, 1, 1);   // hi * [P_hi | P_lo]
       constexpr uint32_t id_half = u_idesc(kUDBlock, kUQ, 1, 1);       // lo * P_hi
+      if constexpr (!CHUNKED) {
       for (int t = 0; t < ntasks && nact > 0; ++t) {
         const int buf = t & 1;
         if (t >= 2) {
@@ -636,11 +640,43 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         }
         u_commit(&sm.acc_full[buf]);
       }
+      } else {
+      // unit u = (d-block task, chunk of kBChunk row blocks); consecutive units alternate TMEM accumulators so that
+      // no fp32 accumulation chain in the tensor core is longer than kBChunk * 8 MMAs (its adds truncate)
+      for (int u = 0; nact > 0 && u < ntasks * nchunks; ++u) {
+        const int t = u / nchunks, c = u - t * nchunks;
+        const int buf = u & 1;
+        if (u >= 2) {
+          u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((u >> 1) + 1) & 1));
+          u_fence_after();
+        }
+        const uint32_t acc = tmem + (uint32_t)(buf * kUStack);
+        const int j0 = c * kBChunk, j1 = min(nact, j0 + kBChunk);
+        for (int i = j0; i < j1; ++i) {
+          const int it = t * nact + i;
+          const int s = it % kUStages;
+          u_mbar_wait(&sm.full[s], (uint32_t)((it / kUStages) & 1));
+          u_fence_after();
+          const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < kUK / 16; ++kk) {
+            const uint64_t b = u_desc(base + kk * 2048, 8192, 1024);                    // P^T, MN-major
+            const uint64_t ah = u_desc(base + kTileBytes + kk * 2048, 8192, 1024);      // bank^T, MN-major
+            const uint64_t al = u_desc(base + 2 * kTileBytes + kk * 2048, 8192, 1024);
+            u_mma(acc, ah, b, id_full, (i > j0 || kk > 0) ? 1u : 0u);
+            if (use_lo) u_mma(acc, al, b, id_half, 1u);
+          }
+          u_commit(&sm.empty[s]);
+        }
+        u_commit(&sm.acc_full[buf]);
+      }
+      }
     }
   } else {
-    // epilogue: TMEM lane = d within the block, column = stacked query row
     const int lq = warp & 3;
     float msum = 0.f;
+    if constexpr (!CHUNKED) {
+    // epilogue: TMEM lane = d within the block, column = stacked query row
 #pragma unroll 1
     for (int t = 0; t < ntasks; ++t) {
     const int buf = t & 1;
@@ -703,6 +739,78 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     if (lane == 0 && nact > 0)
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
     }   // tasks
+    } else {
+    // epilogue: TMEM lane = d within the block, column = stacked query row; running fp32 sums over the chunks
+    float sum[kUQ];
+#pragma unroll
+    for (int j = 0; j < kUQ; ++j) sum[j] = 0.f;
+    const int nunits = nact > 0 ? ntasks * nchunks : ntasks;     // nothing to read when no row block matters
+#pragma unroll 1
+    for (int u = 0; u < nunits; ++u) {
+      const int t = nact > 0 ? u / nchunks : u;
+      const int c = nact > 0 ? u - t * nchunks : 0;
+      const int buf = u & 1;
+      if (nact > 0) {
+        u_mbar_wait(&sm.acc_full[buf], (uint32_t)((u >> 1) & 1));
+        u_fence_after();
+        const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kUStack);
+#pragma unroll
+        for (int cq = 0; cq < kUQ / 32; ++cq) {
+          float a[32], b[32];
+          u_tmem_ld32(tl + (uint32_t)(cq * 32), a);            // hi*P_hi + lo*P_hi, queries [32cq, 32cq+32)
+          u_tmem_ld32(tl + (uint32_t)(kUQ + cq * 32), b);      // hi*P_lo
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[cq * 32 + j] += a[j] + b[j];
+        }
+        u_fence_before();
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
+      }
+      if (c != nchunks - 1 && nact > 0) continue;
+      // ---- last chunk of this d-block: write it out
+      const int64_t d = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock + lq * 32 + lane;
+      if (epi.z) {
+#pragma unroll
+        for (int cq = 0; cq < kUQ / 32; ++cq) {
+          float xv[32], dn[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int q = min(cq * 32 + j, Q - 1);
+            dn[j] = __ldg(epi.z + q) + epi.eps;
+            xv[j] = epi.x0 ? __ldcg(epi.x0 + (int64_t)q * D + d) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int q = cq * 32 + j;
+            if (q < Q) {
+              const float v = sum[cq * 32 + j];
+              const int64_t o = (int64_t)q * D + d;
+              const float n = v / dn[j];
+              if (num) num[o] = v;
+              if (epi.neg_out) epi.neg_out[o] = n;
+              if (epi.x0) epi.x0[o] = fmaf(-epi.scale, n, xv[j]);
+              msum += fminf(fmaxf(n, -1e10f), 1e10f);
+              if (blockIdx.x == 0 && lq == 0 && lane == 0) {
+                if (epi.denom_out) epi.denom_out[q] = dn[j];
+                if (epi.gate_out) epi.gate_out[q] = (!(epi.flags & SDN_EPI_GATE) || dn[j] > epi.gate_thr) ? 1 : 0;
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kUQ; ++j) {
+          if (j < Q) {
+            float* o = num + (int64_t)j * D + d;
+            if (use_atomic) atomicAdd(o, sum[j]); else *o = sum[j];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kUQ; ++j) sum[j] = 0.f;
+    }   // units
+    }
     if (epi.z && epi.mean_out) {
       msum = warp_sum(msum);
       if (lane == 0) atomicAdd(epi.mean_out, msum * epi.inv_qd);
@@ -849,7 +957,8 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   static bool configured = false;
   if (!configured) {
     SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
-    SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+    SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+    SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
     configured = true;
   }
   char* w = static_cast<char*>(ws);
@@ -953,11 +1062,20 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   }
   pid = g_prof.begin("k_umma_accum", st);
   const int gridx = nsplit == 1 ? std::min(dblocks, kNumSMs) : dblocks;
-  k_umma_accum<<<dim3(gridx, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
+  // chains longer than kBChunk row blocks are split over the two TMEM accumulators (fp32 register drain)
+  if ((rblocks + nsplit - 1) / nsplit > kBChunk) {
+    k_umma_accum<true><<<dim3(gridx, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
                                                                      nsplit, nsplit > 1 ? 1 : 0, bf16_bank ? 0 : 1,
                                                                      sparse ? lists.flags : nullptr,
                                                                      sparse ? lists.count : nullptr,
                                                                      sparse ? lists.dense : nullptr, e);
+  } else {
+    k_umma_accum<false><<<dim3(gridx, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
+                                                                     nsplit, nsplit > 1 ? 1 : 0, bf16_bank ? 0 : 1,
+                                                                     sparse ? lists.flags : nullptr,
+                                                                     sparse ? lists.count : nullptr,
+                                                                     sparse ? lists.dense : nullptr, e);
+  }
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;

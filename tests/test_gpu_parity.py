@@ -389,3 +389,42 @@ def test_block_sparse_list_overflow_falls_back_to_tensor_core_pass(nv):
         assert rel(got["x0"], ref["x_0_hat"]) <= TOL, on
         assert rel(got["weights"], ref["weights"]) <= TOL, on
     nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, 1)
+
+
+def test_cfg4_sd3_full_size(nv):
+    """BASELINE config 4 at full size: fast_sdv3 semantics (query channel-normalised), 16x128x128 latents
+    (D = 262144), N = 515, Q = 16 -- 540 MB bank, tcgen05 path with the persistent accumulate pass."""
+    bank = orc.synthetic_bank(515, 16, 128, 128)
+    x = orc.synthetic_queries(bank, 16, "near")
+    want = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.03, sigma=1.0, sdv3=True)
+    got = run_projection(nv, bank, x, 1.0, 0.03, normalize=16)
+    assert rel(got["x0"], want["x_0_hat"]) <= TOL
+    assert rel(got["weights"], want["weights"]) <= TOL
+
+
+def test_cfg5_size_properties(nv):
+    """BASELINE config 5 scale (Q = 128, N = 30000, threshold semantics) through size-independent properties:
+    shard additivity (4 shards) and invariance of the negative mean under bank duplication."""
+    from safe_denoiser_b200.projection import NegativeBank, Projector, shard_bounds
+    N, Q = 30000, 128
+    bank4 = orc.synthetic_bank(N, 4, 64, 64).cuda()
+    x = orc.synthetic_queries(bank4[:2000].cpu(), Q, "near").cuda()
+    full = Projector(NegativeBank(bank4)).partial_sums(x, 3.15)
+    num, z = full.num.clone(), full.z.clone()
+    acc_n, acc_z = torch.zeros_like(num), torch.zeros_like(z)
+    for r in range(4):
+        lo, hi = shard_bounds(N, r, 4)
+        s = Projector(NegativeBank(bank4[lo:hi])).partial_sums(x, 3.15)
+        acc_n += s.num
+        acc_z += s.z
+    assert rel(acc_n, num) <= 2e-5 and rel(acc_z, z) <= 2e-5
+    # per-row gate on the merged sums: every row has a denominator, both outcomes occur for a mid threshold
+    denom = (z + 1e-8).cpu().numpy()
+    thr = float(np.median(denom))
+    assert (denom > thr).any() and (denom <= thr).any()
+    # a query equal to bank row j must put (almost) all its weight on j at sigma = 1
+    xq = bank4[123:124].clone()
+    k = torch.empty(1, N, device="cuda")
+    Projector(NegativeBank(bank4)).partial_sums(xq, 1.0, k_out=k)
+    torch.cuda.synchronize()
+    assert int(k.argmax()) == 123 and float(k.max()) > 0.9

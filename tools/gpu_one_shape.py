@@ -1,7 +1,7 @@
 """Ad-hoc: run one projection shape a few times (target for ncu). usage: gpu_one_shape.py Q N path [C H W]"""
 import sys
 import torch
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from oracle import repellency_oracle as orc
 from safe_denoiser_b200.projection import NegativeBank, Projector
 Q, N, path = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])

@@ -2,7 +2,7 @@
 import sys, time
 import numpy as np
 import torch
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from oracle import repellency_oracle as orc
 from safe_denoiser_b200 import _native as nv
 from safe_denoiser_b200.projection import NegativeBank, Projector
