@@ -91,6 +91,13 @@ int32_t sdn_profile_read(int32_t index, char* name_out, int32_t name_cap, float*
 int sdn_bank_prepare(const float* bank, int64_t N, int64_t D,
                      float* sqnorm_out, void* planes_out, void* stream);
 
+/* Bank build from raw VAE latents [N][C][HW] (RepellencyMethod.project, fast.py:45-70): divides every pixel by its
+ * L2 norm over the C channels (so that ||n_i||^2 = HW) and produces bank_out [N][C*HW] fp32 -- the tensor the
+ * proj_ref cache stores -- together with sqnorm_out and (optionally) the planes, in one pass.  bank_out may alias
+ * latents. */
+int sdn_bank_build(const float* latents, int64_t N, int32_t C, int64_t HW,
+                   float* bank_out, float* sqnorm_out, void* planes_out, void* stream);
+
 /* ---- query ------------------------------------------------------------------------------
  * x0 = c_x * x_in + c_m * model_out   (model_out may be NULL -> x0 = c_x * x_in)
  *   DDPM eps-prediction (diffusers DDPMScheduler.step -> pred_original_sample, called at
@@ -208,9 +215,11 @@ int sdn_shard_merge_correct(const void* const* peer_packed, void* const* peer_ou
  * dist_out [Q,N] = ||x_q - n_i|| from the same expansion; the force is
  *   term_q = sum_i relu(radius/d_qi - 1) (x_q - n_i) ; x0_inout += scale * term.
  * wsum_out [Q] = sum_i relu(radius/d_qi - 1)  (is_negation = wsum != 0, threshold.py:447-450).
+ * xq (may be NULL = x0_inout) is the query the distances and the force are taken on; fast_sdv3.py:332 takes them on
+ * the channel-normalised query while the update still lands on the un-normalised x0.  xsq = ||xq||^2.
  */
 int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t D,
-                     float* x0_inout, const float* xsq, int64_t Q,
+                     float* x0_inout, const float* xq, const float* xsq, int64_t Q,
                      float radius, float scale,
                      float* term_out, float* wsum_out,
                      void* workspace, size_t workspace_bytes, void* stream);

@@ -137,7 +137,7 @@ def empirical_beta(noisy_by_t, bank4, sigma, eps=1e-8, quantile=0.0):
     return out
 
 
-def sparse_repellency(x4, bank4, radius, scale=1.0):
+def sparse_repellency(x4, bank4, radius, scale=1.0, normalise_query=False):
     """SPELL baseline, fast.py:306-340 / threshold.py:415-454.
 
     Neighbours are selected with the FIRST query row broadcast against the
@@ -147,7 +147,9 @@ def sparse_repellency(x4, bank4, radius, scale=1.0):
     within ``radius`` of row q.  term_q = sum_i relu(radius/d_qi - 1) (x_q - n_i);
     x0' = x0 + scale * term.
     """
-    xf = _flat64(x4)
+    x_orig = _flat64(x4)
+    # fast_sdv3.py:332: the force is taken on the channel-normalised query, the update lands on the original x0
+    xf = _flat64(channel_normalise(x4)) if normalise_query else x_orig
     bf = _flat64(bank4)
     # ||x - n|| computed directly (no expansion), as the reference does
     d = np.stack([np.sqrt(((xq[None, :] - bf) ** 2).sum(1)) for xq in xf], 0)
@@ -155,7 +157,7 @@ def sparse_repellency(x4, bank4, radius, scale=1.0):
     with np.errstate(divide="ignore"):
         w = np.where(inside, np.maximum(radius / d - 1.0, 0.0), 0.0)
     term = w.sum(1)[:, None] * xf - w @ bf
-    x0 = xf + scale * term
+    x0 = x_orig + scale * term
     return {"x_0_hat": x0.reshape(np.shape(x4)), "term": term.reshape(np.shape(x4)),
             "trunc_weight": w, "force_norm": float(np.sqrt((term ** 2).sum())),
             "is_negation": bool(w.sum() != 0.0)}

@@ -25,6 +25,7 @@ SIGNATURES = {
     "sdn_profile_enable": (None, [_i32]),
     "sdn_profile_read": (_i32, [_i32, C.c_char_p, _i32, C.POINTER(C.c_float)]),
     "sdn_bank_prepare": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
+    "sdn_bank_build": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
     "sdn_query_prepare": (C.c_int, [_p, _p, _f, _f, _i64, _i64, _i32, _p, _p, _p, _p]),
     "sdn_repel_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "sdn_repel_partial": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _i64, _f, _i32, _f,
@@ -39,7 +40,7 @@ SIGNATURES = {
                                          _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sdn_shard_merge_correct": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i64, _i64, _f, _f, _f, _i32,
                                           _p, _p, _p, _p, _p]),
-    "sdn_sparse_repel": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _f, _f, _p, _p, _p, _sz, _p]),
+    "sdn_sparse_repel": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _f, _f, _p, _p, _p, _sz, _p]),
     "sdn_conditioning_host": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _i32, _f, _i32, _f, _f, _f,
                                         _p, _i32, _p]),
     "sdn_host_release": (None, []),

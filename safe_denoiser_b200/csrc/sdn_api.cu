@@ -154,7 +154,7 @@ int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* p
 }
 
 int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t D, float* x0_inout,
-                     const float* xsq, int64_t Q, float radius, float scale, float* term_out,
+                     const float* xq, const float* xsq, int64_t Q, float radius, float scale, float* term_out,
                      float* wsum_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!bank || !sqnorm || !x0_inout || !xsq || !wsum_out || !workspace) return SDN_E_NULL;
   if (Q <= 0 || N <= 0 || D <= 0 || Q > 65535) return SDN_E_SHAPE;
@@ -166,13 +166,15 @@ int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t 
   cudaStream_t st = (cudaStream_t)stream;
   float* S = static_cast<float*>(workspace);
   float* num = reinterpret_cast<float*>(static_cast<char*>(workspace) + s_bytes);
-  int rc = generic_dots(bank, N, D, x0_inout, Q, S, st);
+  const float* query = xq ? xq : x0_inout;
+  if (!aligned16(query)) return SDN_E_ALIGN;
+  int rc = generic_dots(bank, N, D, query, Q, S, st);
   if (rc) return rc;
   rc = sparse_weights(S, sqnorm, xsq, Q, N, radius, wsum_out, st);
   if (rc) return rc;
   rc = generic_accum(bank, N, D, S, Q, num, st);
   if (rc) return rc;
-  return sparse_apply(num, wsum_out, Q, D, scale, x0_inout, term_out, st);
+  return sparse_apply(num, wsum_out, Q, D, scale, query, x0_inout, term_out, st);
 }
 
 // ------------------------------------------------------------------ host-buffer path (e2e)

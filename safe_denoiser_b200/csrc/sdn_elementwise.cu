@@ -37,6 +37,40 @@ k_bank_prepare(const float* __restrict__ bank, int64_t N, int64_t D, float* __re
   if (lane == 0) sqnorm[i] = s;
 }
 
+// Bank build (RepellencyMethod.project, fast.py:45-70, after the VAE): per-pixel channel L2-normalisation of the
+// raw latents fused with ||n_i||^2 and the bf16 planes -- one pass instead of norm + div + the prepare pass.
+// One thread per pixel, channels strided by HW.
+__global__ void __launch_bounds__(256)
+k_bank_build(const float* __restrict__ latents, int64_t HW, int C, float* __restrict__ bank,
+             float* __restrict__ sqnorm, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float red[33];
+  const int64_t n = blockIdx.y;
+  const int64_t base = n * HW * C;
+  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  float s = 0.f;
+  if (p < HW) {
+    float ss = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = latents[base + (int64_t)c * HW + p];
+      ss = fmaf(v, v, ss);
+    }
+    const float nrm = sqrtf(ss);
+    for (int c = 0; c < C; ++c) {
+      const int64_t o = base + (int64_t)c * HW + p;
+      const float u = latents[o] / nrm;
+      bank[o] = u;
+      if (hi) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(u);
+        hi[o] = h;
+        lo[o] = __float2bfloat16_rn(u - __bfloat162float(h));
+      }
+      s = fmaf(u, u, s);
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(sqnorm + n, s);
+}
+
 // ---------------------------------------------------------------- query prepare
 __global__ void __launch_bounds__(256)
 k_query_prepare(const float* __restrict__ x_in, const float* __restrict__ m, float c_x, float c_m,
@@ -222,6 +256,19 @@ int sdn_bank_prepare(const float* bank, int64_t N, int64_t D, float* sqnorm_out,
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(planes_out);
   __nv_bfloat16* lo = hi ? hi + N * D : nullptr;
   k_bank_prepare<<<(unsigned)cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(bank, N, D, sqnorm_out, hi, lo);
+  SDN_LAUNCHED();
+  return SDN_OK;
+}
+
+int sdn_bank_build(const float* latents, int64_t N, int32_t C, int64_t HW, float* bank_out, float* sqnorm_out,
+                   void* planes_out, void* stream) {
+  if (!latents || !bank_out || !sqnorm_out) return SDN_E_NULL;
+  if (N <= 0 || C <= 0 || HW <= 0 || N > 65535) return SDN_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  SDN_CUDA_OK(cudaMemsetAsync(sqnorm_out, 0, sizeof(float) * N, st));
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(planes_out);
+  __nv_bfloat16* lo = hi ? hi + N * C * HW : nullptr;
+  k_bank_build<<<dim3((unsigned)cdiv(HW, 256), (unsigned)N), 256, 0, st>>>(latents, HW, C, bank_out, sqnorm_out, hi, lo);
   SDN_LAUNCHED();
   return SDN_OK;
 }

@@ -162,15 +162,16 @@ k_accum(const float* __restrict__ bank, int64_t N, int64_t D, const float* __res
 
 __global__ void __launch_bounds__(256)
 k_sparse_apply(const float* __restrict__ num, const float* __restrict__ wsum, int64_t D, float scale,
-               float* __restrict__ x0, float* __restrict__ term_out) {
+               const float* xq, float* x0, float* __restrict__ term_out) {
   const int64_t q = blockIdx.y;
   const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (j >= D) return;
   const float ws = wsum[q];
   float4 x = *reinterpret_cast<const float4*>(x0 + q * D + j);
+  const float4 xf = *reinterpret_cast<const float4*>(xq + q * D + j);   // the query the force is taken on
   const float4 s = *reinterpret_cast<const float4*>(num + q * D + j);
   // sum_i w_i (x - n_i) = (sum w) x - sum_i w_i n_i      (fast.py:321-328)
-  float4 t = make_float4(fmaf(ws, x.x, -s.x), fmaf(ws, x.y, -s.y), fmaf(ws, x.z, -s.z), fmaf(ws, x.w, -s.w));
+  float4 t = make_float4(fmaf(ws, xf.x, -s.x), fmaf(ws, xf.y, -s.y), fmaf(ws, xf.z, -s.z), fmaf(ws, xf.w, -s.w));
   x.x = fmaf(scale, t.x, x.x);
   x.y = fmaf(scale, t.y, x.y);
   x.z = fmaf(scale, t.z, x.z);
@@ -212,9 +213,9 @@ int sparse_weights(float* S, const float* sqnorm, const float* xsq, int64_t Q, i
   return SDN_OK;
 }
 
-int sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale,
+int sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale, const float* xq,
                  float* x0_inout, float* term_out, cudaStream_t st) {
-  k_sparse_apply<<<dim3((unsigned)cdiv(D, 1024), (unsigned)Q), 256, 0, st>>>(num, wsum, D, scale, x0_inout,
+  k_sparse_apply<<<dim3((unsigned)cdiv(D, 1024), (unsigned)Q), 256, 0, st>>>(num, wsum, D, scale, xq, x0_inout,
                                                                               term_out);
   SDN_LAUNCHED();
   return SDN_OK;

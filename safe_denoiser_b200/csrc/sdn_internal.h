@@ -17,7 +17,7 @@ int generic_accum(const float* bank, int64_t N, int64_t D, const float* k, int64
 // in place: S[q,i] -> relu(radius / d_qi - 1) ; wsum[q] = sum_i of that   (SPELL)
 int sparse_weights(float* S, const float* sqnorm, const float* xsq, int64_t Q, int64_t N,
                    float radius, float* wsum, cudaStream_t st);
-int sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale,
+int sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale, const float* xq,
                  float* x0_inout, float* term_out, cudaStream_t st);
 
 // ---- one-pass cluster path for GEMV-shaped calls (sdn_stream.cu) ----

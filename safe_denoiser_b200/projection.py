@@ -44,6 +44,24 @@ class NegativeBank:
         nv.check(nv.lib().sdn_bank_prepare(nv.ptr(self.flat), self.N, self.D, nv.ptr(self.sqnorm),
                                            nv.ptr(self.planes), nv.current_stream()))
 
+    @classmethod
+    def from_latents(cls, latents: torch.Tensor, with_planes: bool = False) -> "NegativeBank":
+        """Build the bank from raw VAE latents [N,C,H,W]: per-pixel channel normalisation (``project``,
+        fast.py:55-56), ||n_i||^2 and the planes in one fused pass.  ``.tensor`` is what the proj_ref cache stores."""
+        if not latents.is_cuda or latents.dim() != 4:
+            raise RuntimeError("from_latents needs a CUDA tensor [N,C,H,W]")
+        lat = latents.float().contiguous()
+        n, c, h, w = lat.shape
+        self = cls.__new__(cls)
+        self.tensor = torch.empty_like(lat)
+        self.N, self.D, self.item_shape = n, c * h * w, (c, h, w)
+        self.flat = self.tensor.view(n, self.D)
+        self.sqnorm = torch.empty(n, dtype=torch.float32, device=lat.device)
+        self.planes = torch.empty(2, n, self.D, dtype=torch.bfloat16, device=lat.device) if with_planes else None
+        nv.check(nv.lib().sdn_bank_build(nv.ptr(lat), n, c, h * w, nv.ptr(self.flat), nv.ptr(self.sqnorm),
+                                         nv.ptr(self.planes), nv.current_stream()))
+        return self
+
     @property
     def device(self):
         return self.tensor.device
@@ -336,19 +354,22 @@ class Projector:
                                             nv.current_stream()))
         return out.view_as(x), s
 
-    def sparse(self, x0: torch.Tensor, radius: float, scale: float, want_term: bool = False):
-        """SPELL baseline (fast.py:306-340): x0 += scale * sum_i relu(radius/d_i - 1)(x0 - n_i) in place.
-        Returns (term or None, wsum [Q])."""
+    def sparse(self, x0: torch.Tensor, radius: float, scale: float, want_term: bool = False,
+               normalize_channels: int = 0):
+        """SPELL baseline (fast.py:306-340): x0 += scale * sum_i relu(radius/d_i - 1)(xq - n_i) in place, where xq is
+        x0, or x0 channel-normalised (fast_sdv3.py:332).  Returns (term or None, wsum [Q])."""
         L, st = nv.lib(), nv.current_stream()
         Q, xf = self._flat_query(x0)
-        s = self._get(Q, False)
+        s = self._get(Q, normalize_channels > 0)
         b = self.bank
-        nv.check(L.sdn_query_prepare(nv.ptr(xf), None, 1.0, 0.0, Q, b.D, 0, None, None, nv.ptr(s.xsq), st))
+        xq = s.xq if normalize_channels > 0 else None
+        nv.check(L.sdn_query_prepare(nv.ptr(xf), None, 1.0, 0.0, Q, b.D, int(normalize_channels), None, nv.ptr(xq),
+                                     nv.ptr(s.xsq), st))
         need = Q * b.N * 4 + Q * b.D * 4 + 1024
         ws = torch.empty(need, dtype=torch.uint8, device=b.device)
         term = torch.empty_like(xf) if want_term else None
         wsum = torch.empty(Q, dtype=torch.float32, device=b.device)
-        nv.check(L.sdn_sparse_repel(nv.ptr(b.flat), nv.ptr(b.sqnorm), b.N, b.D, nv.ptr(xf), nv.ptr(s.xsq), Q,
+        nv.check(L.sdn_sparse_repel(nv.ptr(b.flat), nv.ptr(b.sqnorm), b.N, b.D, nv.ptr(xf), nv.ptr(xq), nv.ptr(s.xsq), Q,
                                     float(radius), float(scale), nv.ptr(term), nv.ptr(wsum),
                                     nv.ptr(ws), need, st))
         return term, wsum

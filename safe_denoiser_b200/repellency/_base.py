@@ -126,6 +126,8 @@ class RepellencyBase:
             latents = torch.cat(parts, 0)
         else:
             latents = self.embed_fn(data)
+        if latents.is_cuda and latents.dim() == 4 and latents.dtype == torch.float32:
+            return NegativeBank.from_latents(latents).tensor          # fused normalise (+ ||n||^2) kernel
         latents = latents / torch.norm(latents, dim=1, keepdim=True)
         return latents.float() if self.float_after_project else latents
 

@@ -93,7 +93,8 @@ class Sparse(FastRepellencyMethod):
     def repellency_force(self, x_0_hat, **kwargs):
         """-> (sum_i relu(radius/d_i - 1)(x - n_i), its L2 norm); x_0_hat is not modified."""
         q, _ = self._as_query(x_0_hat)
-        term, _ = self.projector().sparse(q.clone(), self.radius, 0.0, want_term=True)
+        term, _ = self.projector().sparse(q.clone(), self.radius, 0.0, want_term=True,
+                                          normalize_channels=self._channels())
         return term.view_as(x_0_hat), LazyScalar(term.norm(p=2))
 
     def empirical_denoiser(self, x_0_hat, **kwargs):
@@ -101,7 +102,8 @@ class Sparse(FastRepellencyMethod):
 
     def conditioning_1(self, x_0_hat, **kwargs):
         q, copied = self._as_query(x_0_hat)
-        term, _ = self.projector().sparse(q, self.radius, self.scale, want_term=True)
+        term, _ = self.projector().sparse(q, self.radius, self.scale, want_term=True,
+                                          normalize_channels=self._channels())
         if copied:
             x_0_hat.copy_(q)
         return {"x_0_hat": x_0_hat, "mean_x_0_hat": LazyScalar(term.norm(p=2))}

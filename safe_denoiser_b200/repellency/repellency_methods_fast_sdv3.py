@@ -34,9 +34,8 @@ class RandomNoiseRepellency(RandomNoise, RepellencyMethod):
 
 @register_conditioning_method(name='sparse')
 class SparseRepellency(Sparse, RepellencyMethod):
-    # fast_sdv3.py:332 normalises the query inside repellency_force; the SPELL force is then taken
-    # on the normalised query.  Not on the README's SD3 command lines; kept un-normalised here.
-    normalize_query = False
+    # fast_sdv3.py:332: distances and force are taken on the channel-normalised query, the update lands on x0
+    normalize_query = True
 
 
 @register_conditioning_method(name='lsh')

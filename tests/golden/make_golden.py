@@ -130,6 +130,22 @@ def sparse_cases(out):
                     out[key + "/is_negation"] = np.bool_(d["is_negation"])
 
 
+def sparse_sdv3_cases(out):
+    c, h, w, n = 16, 4, 4, 29
+    bank = synthetic_bank(n, c, h, w, seed=1234)
+    out["sparse_sdv3/bank"] = bank.numpy()
+    for radius in (5.0, 5.7, 6.5):
+        proc = build(ref_sdv3, "sparse", bank, scale=1.6, radius=radius)
+        for regime in ("near", "x0", "mid"):
+            x = synthetic_queries(bank, 1, regime, seed=7) * 1.7       # un-normalised query
+            xin = x.clone()
+            d = proc.conditioning(xin, beta_threshold=False)
+            key = f"sparse_sdv3/r{radius}/{regime}"
+            out[key + "/x"] = x.numpy()
+            out[key + "/x0"] = d["x_0_hat"].numpy()
+            out[key + "/item"] = np.float64(d["mean_x_0_hat"])
+
+
 def known_answers():
     """Scalars at the real SD-1.4 shape (SURVEY 8c recipe)."""
     g = torch.Generator().manual_seed(1234)
@@ -175,6 +191,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "beta_cases.npz"), **fx)
     fx = {}
     sparse_cases(fx)
+    sparse_sdv3_cases(fx)
     np.savez_compressed(os.path.join(HERE, "sparse_cases.npz"), **fx)
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(known_answers(), f, indent=1)

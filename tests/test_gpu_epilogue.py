@@ -122,3 +122,19 @@ def test_query_prepare_eps_to_x0_and_channel_norm():
     assert rel(x0, want0.cpu().numpy()) <= 1e-6
     assert rel(xq, wantq) <= 1e-5
     assert rel(xsq, (wantq ** 2).sum(1)) <= 1e-5
+
+
+def test_bank_build_from_latents_matches_project():
+    """sdn_bank_build == RepellencyMethod.project's normalisation (fast.py:55-56) + sdn_bank_prepare."""
+    from safe_denoiser_b200.projection import NegativeBank
+    g = torch.Generator().manual_seed(9)
+    lat = torch.randn(33, 4, 16, 16, generator=g) * 3.0
+    want = (lat / lat.norm(dim=1, keepdim=True)).double()
+    bank = NegativeBank.from_latents(lat.cuda(), with_planes=True)
+    torch.cuda.synchronize()
+    assert rel(bank.tensor, want.numpy()) <= 1e-6
+    assert rel(bank.sqnorm, (want.reshape(33, -1) ** 2).sum(1).numpy()) <= 1e-5
+    ref = NegativeBank(bank.tensor.clone(), with_planes=True)
+    assert torch.equal(ref.planes, bank.planes)
+    recon = bank.planes[0].float() + bank.planes[1].float()
+    assert rel(recon, bank.flat.cpu().numpy()) <= 2e-5

@@ -210,6 +210,19 @@ def test_dropin_sparse_against_reference_goldens(tmp_path):
                     assert bool(d["is_negation"]) == bool(fx[key + "/is_negation"])
 
 
+def test_dropin_sparse_sdv3_against_reference_goldens(tmp_path):
+    fx = np.load(os.path.join(G, "sparse_cases.npz"))
+    for radius in (5.0, 5.7, 6.5):
+        proc = _build("fast_sdv3", "sparse", fx["sparse_sdv3/bank"], tmp_path, scale=1.6, radius=radius)
+        for regime in ("near", "x0", "mid"):
+            key = f"sparse_sdv3/r{radius}/{regime}"
+            xin = torch.from_numpy(fx[key + "/x"]).cuda()
+            d = proc.conditioning(xin, beta_threshold=False)
+            assert rel(xin, fx[key + "/x0"]) <= TOL, key
+            want = float(fx[key + "/item"])
+            assert abs(float(d["mean_x_0_hat"]) - want) <= 2e-3 * max(1.0, want)
+
+
 def test_empirical_beta_against_reference_goldens(tmp_path):
     fx = np.load(os.path.join(G, "beta_cases.npz"))
     proc = _build("threshold", "kernel_fast", fx["beta/bank"], tmp_path, scale=0.33, sigma=3.15,

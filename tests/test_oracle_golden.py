@@ -97,6 +97,14 @@ def test_sparse_matches_reference():
                     assert r["is_negation"] == bool(fx[key + "/is_negation"])
                     outcomes.add(r["is_negation"])
     assert outcomes == {True, False}
+    # SD3 variant: force on the channel-normalised query, update on the original (fast_sdv3.py:332)
+    bank3 = fx["sparse_sdv3/bank"]
+    for radius in (5.0, 5.7, 6.5):
+        for regime in ("near", "x0", "mid"):
+            key = f"sparse_sdv3/r{radius}/{regime}"
+            r = orc.sparse_repellency(fx[key + "/x"], bank3, radius, scale=1.6, normalise_query=True)
+            assert rel(r["x_0_hat"], fx[key + "/x0"]) < 2e-5, key
+            assert abs(r["force_norm"] - float(fx[key + "/item"])) <= 2e-4 * max(1.0, r["force_norm"])
 
 
 def test_known_answers_sd14_shape():
