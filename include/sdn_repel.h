@@ -123,6 +123,10 @@ int sdn_query_prepare(const float* x_in, const float* model_out, float c_x, floa
  * N-sharding: run this per shard, all-reduce(sum) num_out and z_out, then call an epilogue.
  */
 size_t sdn_repel_workspace_bytes(int64_t Q, int64_t N, int64_t D, int32_t path);
+/* Which kernel family sdn_repel_partial would run for this shape (SDN_PATH_*), given whether planes exist.
+ * xsq may be NULL in sdn_repel_partial when the answer is SDN_PATH_STREAM or SDN_PATH_UMMA(_BF16): those kernels
+ * compute ||xq||^2 themselves, which saves the sdn_query_prepare launch for a plain query. */
+int32_t sdn_repel_path(int64_t Q, int64_t N, int64_t D, int32_t has_planes, int32_t path);
 
 int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes,
                       int64_t N, int64_t D,

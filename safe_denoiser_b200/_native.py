@@ -28,6 +28,7 @@ SIGNATURES = {
     "sdn_bank_build": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
     "sdn_query_prepare": (C.c_int, [_p, _p, _f, _f, _i64, _i64, _i32, _p, _p, _p, _p]),
     "sdn_repel_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
+    "sdn_repel_path": (_i32, [_i64, _i64, _i64, _i32, _i32]),
     "sdn_repel_partial": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _i64, _f, _i32, _f,
                                     _p, _p, _p, _p, _sz, _i32, _p]),
     "sdn_epilogue_correct": (C.c_int, [_p, _p, _i64, _i64, _f, _f, _f, _i32, _p, _p, _p, _p, _p, _p]),

@@ -70,6 +70,12 @@ int32_t sdn_profile_read(int32_t index, char* name_out, int32_t name_cap, float*
   return 1;
 }
 
+int32_t sdn_repel_path(int64_t Q, int64_t N, int64_t D, int32_t has_planes, int32_t path) {
+  if (Q <= 0 || N <= 0 || D <= 0) return SDN_E_SHAPE;
+  static const char dummy = 0;
+  return pick_path(path, Q, N, D, has_planes ? &dummy : nullptr);
+}
+
 size_t sdn_repel_workspace_bytes(int64_t Q, int64_t N, int64_t D, int32_t path) {
   if (Q <= 0 || N <= 0 || D <= 0) return 0;
   size_t need = generic_workspace_bytes(Q, N);
@@ -83,7 +89,7 @@ int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes
                       const float* xq, const float* xsq, int64_t Q, float inv_two_sigma_sq,
                       int32_t dist_power, float bank_alpha, float* num_out, float* z_out, float* k_out,
                       void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
-  if (!sqnorm || !xq || !xsq || !z_out) return SDN_E_NULL;  // num_out NULL: z only (empirical_beta)
+  if (!sqnorm || !xq || !z_out) return SDN_E_NULL;  // num_out NULL: z only (empirical_beta)
   if (!bank && !planes) return SDN_E_NULL;
   if (Q <= 0 || N <= 0 || D <= 0 || Q > 65535) return SDN_E_SHAPE;
   if (dist_power != 1 && dist_power != 2) return SDN_E_PARAM;
@@ -107,7 +113,7 @@ int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes
     case SDN_PATH_GENERIC: break;
     default: return SDN_E_PARAM;
   }
-  if (!bank) return SDN_E_NULL;
+  if (!bank || !xsq) return SDN_E_NULL;   // the generic kernels need ||xq||^2 from sdn_query_prepare
   float* S = k_out;
   if (!S) {
     if (!workspace || workspace_bytes < generic_workspace_bytes(Q, N)) return SDN_E_WORKSPACE;

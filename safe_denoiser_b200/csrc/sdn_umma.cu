@@ -912,7 +912,7 @@ int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, 
   if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
   for (int64_t q0 = 0; q0 < Q; q0 += kUQ) {
     const int64_t qn = std::min<int64_t>(kUQ, Q - q0);
-    const int rc = umma_partial_64(planes, sqnorm, N, D, xq + q0 * D, xsq + q0, qn, inv2s2, power, alpha,
+    const int rc = umma_partial_64(planes, sqnorm, N, D, xq + q0 * D, xsq ? xsq + q0 : nullptr, qn, inv2s2, power, alpha,
                                    num ? num + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws,
                                    ws_bytes, st, nullptr, nullptr, bf16_bank);
     if (rc) return rc;

@@ -140,6 +140,7 @@ class Projector:
         self._scratch = {}
         self._graphs = {}
         self._few_launch = {}
+        self._needs_xsq = {}
 
     # -- scratch -----------------------------------------------------------------------------
     def _get(self, Q: int, need_xq: bool) -> _Scratch:
@@ -198,9 +199,17 @@ class Projector:
         if model_out is not None:
             mo = self._flat_query(model_out)[1]
         xo = None if x0_out is None else self._flat_query(x0_out)[1]
-        nv.check(L.sdn_query_prepare(nv.ptr(xf), nv.ptr(mo), c_x, c_m, Q, self.bank.D,
-                                     int(normalize_channels), nv.ptr(xo), nv.ptr(s.xq) if normalize_channels > 0 else None,
-                                     nv.ptr(s.xsq), st))
+        plain = mo is None and normalize_channels == 0 and xo is None and c_x == 1.0
+        key = (Q, z_only, self.bank.planes is not None)
+        if plain and key not in self._needs_xsq:
+            chosen = L.sdn_repel_path(Q, self.bank.N, self.bank.D, 1 if self.bank.planes is not None else 0, self.path)
+            # the generic kernels (also used for z-only calls the one-pass kernel would otherwise take) need ||x||^2
+            self._needs_xsq[key] = chosen == nv.PATH_GENERIC or (z_only and chosen == nv.PATH_STREAM)
+        have_xsq = not (plain and not self._needs_xsq.get(key, True))
+        if have_xsq:
+            nv.check(L.sdn_query_prepare(nv.ptr(xf), nv.ptr(mo), c_x, c_m, Q, self.bank.D, int(normalize_channels),
+                                         nv.ptr(xo), nv.ptr(s.xq) if normalize_channels > 0 else None,
+                                         nv.ptr(s.xsq), st))
         if normalize_channels > 0:
             query = s.xq
         elif xo is not None:
@@ -209,7 +218,7 @@ class Projector:
             query = xf
         b = self.bank
         nv.check(L.sdn_repel_partial(nv.ptr(b.flat), nv.ptr(b.sqnorm), nv.ptr(b.planes), b.N, b.D,
-                                     nv.ptr(query), nv.ptr(s.xsq), Q,
+                                     nv.ptr(query), nv.ptr(s.xsq) if have_xsq else None, Q,
                                      1.0 / (2.0 * float(sigma) ** 2), int(dist_power), float(bank_alpha),
                                      None if z_only else nv.ptr(s.num), nv.ptr(s.z), nv.ptr(k_out),
                                      nv.ptr(s.ws), s.ws_bytes, self.path, st))
