@@ -229,14 +229,20 @@ int sdn_conditioning_host(const float* bank, const float* sqnorm, const void* pl
   void* wsp = p + 3 * qd + 3 * qv;
 
   SDN_CUDA_OK(cudaMemcpyAsync(x0, x0_host, sizeof(float) * Q * D, cudaMemcpyHostToDevice, st));
-  int rc = sdn_query_prepare(x0, nullptr, 1.f, 0.f, Q, D, normalize_C, nullptr,
-                             normalize_C > 0 ? xq : nullptr, xsq, stream);
-  if (rc) return rc;
-  const float* query = normalize_C > 0 ? xq : x0;
-  rc = sdn_repel_partial(bank, sqnorm, planes, N, D, query, xsq, Q, inv_two_sigma_sq, dist_power,
-                         bank_alpha, num, z, nullptr, wsp, ws, path, stream);
-  if (rc) return rc;
-  rc = sdn_epilogue_correct(num, z, Q, D, eps, scale, 0.f, 0, x0, nullptr, denom, nullptr, nullptr, stream);
+  int rc = SDN_E_UNSUPPORTED;
+  if (normalize_C == 0 && path == SDN_PATH_AUTO)      // plain query: the few-launch sequence when the shape allows
+    rc = sdn_conditioning_fused(bank, sqnorm, planes, N, D, x0, Q, inv_two_sigma_sq, dist_power, bank_alpha, eps, scale,
+                                0.f, 0, nullptr, z, nullptr, denom, nullptr, nullptr, nullptr, wsp, ws, stream);
+  if (rc == SDN_E_UNSUPPORTED) {
+    rc = sdn_query_prepare(x0, nullptr, 1.f, 0.f, Q, D, normalize_C, nullptr, normalize_C > 0 ? xq : nullptr, xsq,
+                           stream);
+    if (rc) return rc;
+    const float* query = normalize_C > 0 ? xq : x0;
+    rc = sdn_repel_partial(bank, sqnorm, planes, N, D, query, xsq, Q, inv_two_sigma_sq, dist_power, bank_alpha, num, z,
+                           nullptr, wsp, ws, path, stream);
+    if (rc) return rc;
+    rc = sdn_epilogue_correct(num, z, Q, D, eps, scale, 0.f, 0, x0, nullptr, denom, nullptr, nullptr, stream);
+  }
   if (rc) return rc;
   SDN_CUDA_OK(cudaMemcpyAsync(x0_host, x0, sizeof(float) * Q * D, cudaMemcpyDeviceToHost, st));
   SDN_CUDA_OK(cudaMemcpyAsync(denom_host, denom, sizeof(float) * Q, cudaMemcpyDeviceToHost, st));
