@@ -192,7 +192,8 @@ def main():
     bank = NegativeBank(bank_cpu[lo:hi].to(dev), with_planes=(args.path in (0, 3, 4)))
     proj = Projector(bank, path=args.path, group=group)
     x_src = orc.synthetic_queries(bank_cpu, Q, "near").to(dev)
-    x = x_src.clone()
+    x = proj.query_buffer(Q, tuple(x_src.shape)) if world > 1 else x_src.clone()
+    x.copy_(x_src)
     normalize = C if wl["kind"] == "fast_sdv3" else 0
     sigma, scale, eps = wl["sigma"], wl["scale"], 1e-8
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)

@@ -67,8 +67,12 @@ __global__ void __launch_bounds__(256) k_shard_merge_correct(const MergeArgs a) 
   __syncthreads();
 
   if (tid == 0) {
+    float zp[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) zp[p] = (p < a.world) ? __ldcv(a.packed[p] + a.Q * a.D + q) : 0.f;
     float z = 0.f;
-    for (int p = 0; p < a.world; ++p) z += __ldcv(a.packed[p] + a.Q * a.D + q);
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) z += zp[p];
     const float denom = z + a.eps;
     s_denom = denom;
     if (blockIdx.x == 0) {
@@ -84,18 +88,24 @@ __global__ void __launch_bounds__(256) k_shard_merge_correct(const MergeArgs a) 
   const int64_t v0 = v_all * a.rank / a.world, v1 = v_all * (a.rank + 1) / a.world;
   for (int64_t v = v0 + (int64_t)blockIdx.x * 256 + tid; v < v1; v += (int64_t)gridDim.x * 256) {
     const int64_t o = q * a.D + v * 4;
+    // all peer loads in flight at once (an NVLink load is ~2 us; issued one after the other they dominated the
+    // kernel), then summed in rank order
+    float4 t[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p)
+      t[p] = (p < a.world) ? __ldcv(reinterpret_cast<const float4*>(a.packed[p] + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < a.world; ++p) {
-      const float4 t = __ldcv(reinterpret_cast<const float4*>(a.packed[p] + o));
-      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-    }
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) { s.x += t[p].x; s.y += t[p].y; s.z += t[p].z; s.w += t[p].w; }
     const float4 x = *reinterpret_cast<const float4*>(a.x0 + o);
     float4 r;
     r.x = fmaf(-a.scale, s.x / denom, x.x);
     r.y = fmaf(-a.scale, s.y / denom, x.y);
     r.z = fmaf(-a.scale, s.z / denom, x.z);
     r.w = fmaf(-a.scale, s.w / denom, x.w);
-    for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4*>(a.out[p] + o) = r;
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p)
+      if (p < a.world) *reinterpret_cast<float4*>(a.out[p] + o) = r;
   }
 
   // ---- barrier 2: my stores have landed everywhere; leave only when every peer's stores have landed here
@@ -142,7 +152,7 @@ extern "C" int sdn_shard_merge_correct(const void* const* peer_packed, void* con
   a.gate_thr = gate_threshold; a.flags = flags; a.x0 = x0_local; a.denom_out = denom_out; a.gate_out = gate_out;
   a.counter = static_cast<unsigned int*>(counter);
   const int64_t slice_v = D / 4 / world + 1;
-  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(slice_v, 256), 64));
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(slice_v, 256), 1024));
   k_shard_merge_correct<<<dim3(gx, (unsigned)Q), 256, 0, (cudaStream_t)stream>>>(a);
   SDN_LAUNCHED();
   return SDN_OK;

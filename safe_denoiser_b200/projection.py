@@ -280,10 +280,25 @@ class Projector:
             float(eps), float(scale), float(gate_threshold if gate_threshold is not None else 0.0), flags,
             nv.ptr(xf), nv.ptr(s.denom), nv.ptr(s.gate), nv.ptr(link.counter), nv.current_stream()))
         merged = link.out.view(Q, self.bank.D)
+        if xf.data_ptr() == merged.data_ptr():
+            return s          # the query lives in the peer-mapped buffer (query_buffer): peers wrote it in place
         if self.compute_mean:
             s.mean.copy_(((xf - merged) / (scale if scale != 0 else 1.0)).clamp_(-1e10, 1e10).mean().reshape(1))
         xf.copy_(merged)
         return s
+
+    def query_buffer(self, Q: int, shape=None) -> torch.Tensor:
+        """N-sharded banks: a [Q, D] query tensor that lives in this rank's peer-mapped result buffer.  A query
+        placed there is corrected in place by the merge kernel itself (rank r rewrites D-slice r on every rank), which
+        saves the copy back into a private tensor.  Single GPU: a plain tensor."""
+        D = self.bank.D
+        if self.group is None or not self.fused_merge:
+            t = torch.empty(Q, D, dtype=torch.float32, device=self.bank.device)
+        else:
+            s = self._get(Q, False)
+            t = s.link.out.view(Q, D) if s.link is not None else torch.empty(Q, D, dtype=torch.float32,
+                                                                            device=self.bank.device)
+        return t.view(shape) if shape is not None else t
 
     def correct_graphed(self, x0: torch.Tensor, sigma: float, scale: float, eps: float, **kw):
         """``correct`` replayed from a CUDA graph: the 6-8 small launches of one projection are launch bound

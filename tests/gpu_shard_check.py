@@ -32,7 +32,8 @@ def main():
         for fused in (True, False):
             proj = Projector(NegativeBank(bank4[lo:hi].to(dev)), group=dist.group.WORLD)
             proj.fused_merge = fused
-            x = x4.to(dev).clone()
+            x = proj.query_buffer(Q, tuple(x4.shape)) if fused else x4.to(dev).clone()   # in-place peer-mapped query
+            x.copy_(x4.to(dev))
             _, s = proj.correct(x, 3.15, 0.33, 1e-8, gate_threshold=1.0)
             torch.cuda.synchronize()
             err = float((x - xr).abs().max() / xr.abs().max())
