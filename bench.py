@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--path", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 stream, 3 tcgen05, 4 tcgen05 reading only the bf16 hi plane")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: the bank grows with the GPU count (N x gpus rows, a fixed N-row shard per GPU) -- "
+                         "the scaled-bank sweep of BASELINE configs[4]; default is strong scaling on a fixed bank")
     ap.add_argument("--sparse", action="store_true",
                     help="let the accumulate pass skip bank-row blocks whose weights are below fp32 resolution "
                          "(library default; off here so that the bench measures the dense worst case)")
@@ -145,9 +148,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     Q, N, C, H, W = wl["Q"], wl["N"], wl["C"], wl["H"], wl["W"]
+    if args.weak:
+        N = N * max(1, args.gpus)
     D = C * H * W
     base = {"metric": "repellency projections/sec", "unit": "projections/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak" if args.weak else "strong",
             "vs_baseline": None, "dtype": "bf16 bank planes (opt-in, outside the parity tolerance)" if args.path == 4 else "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "Q": Q, "N": N, "latent": [C, H, W],
@@ -197,6 +203,14 @@ def main():
     normalize = C if wl["kind"] == "fast_sdv3" else 0
     sigma, scale, eps = wl["sigma"], wl["scale"], 1e-8
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
+
+    def flush_l2():
+        # write a buffer larger than L2 (evicts the bank), then READ another one so that the dirty lines of the
+        # write are written back before the timed region starts instead of during it (a 256 MiB memset leaves
+        # ~126 MB of dirty lines whose write-back otherwise steals DRAM bandwidth from the first kernel timed)
+        flush.zero_()
+        flush_rd.sum()
 
     use_graph = not args.no_graph
     proj.compute_mean = False      # the logging scalar costs an extra pass on the sharded path; not part of the metric
@@ -230,7 +244,7 @@ def main():
     barrier()
     for i in range(args.steps):
         x.copy_(x_src)
-        flush.zero_()
+        flush_l2()
         ev0[i].record()
         step()
         ev1[i].record()
@@ -256,15 +270,43 @@ def main():
     nv.profile_enable(True)
     L, st = nv.lib(), nv.current_stream()
     xf = x.view(Q, D)
-    for i in range(args.steps):
-        flush.zero_()
+
+    def stage_once():
+        # query prepare is not part of the stage; the events p0/p1 and the library's per-kernel events bracket
+        # sdn_repel_partial only
         nv.check(L.sdn_query_prepare(nv.ptr(xf), None, 1.0, 0.0, Q, D, normalize, None,
-                                     nv.ptr(s.xq) if normalize else None, nv.ptr(s.xsq), st))
+                                     nv.ptr(s.xq) if normalize else None, nv.ptr(s.xsq), nv.current_stream()))
         query = s.xq if normalize else xf
-        p0[i].record()
         nv.check(L.sdn_repel_partial(nv.ptr(bank.flat), nv.ptr(bank.sqnorm), nv.ptr(bank.planes), bank.N, D,
                                      nv.ptr(query), nv.ptr(s.xsq), Q, 1.0 / (2 * sigma * sigma), 1, 1.0,
-                                     nv.ptr(s.num), nv.ptr(s.z), None, nv.ptr(s.ws), s.ws_bytes, args.path, st))
+                                     nv.ptr(s.num), nv.ptr(s.z), None, nv.ptr(s.ws), s.ws_bytes, args.path,
+                                     nv.current_stream()))
+
+    # Replay the stage from a CUDA graph (the library's event records become graph nodes): the per-kernel intervals
+    # then contain ~1 us of dependency latency instead of an eager launch gap of 5-10 us.  Eager fallback if the
+    # capture is refused.
+    stage_graph = None
+    if not args.no_graph:
+        try:
+            stage_once()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                stage_once()
+            g.replay()
+            torch.cuda.synchronize()
+            if nv.profile_read():
+                stage_graph = g
+        except Exception:
+            stage_graph = None
+            torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush_l2()
+        p0[i].record()
+        if stage_graph is not None:
+            stage_graph.replay()
+        else:
+            stage_once()
         p1[i].record()
         for name, ms in nv.profile_read():
             kernel_ms.setdefault(name, []).append(ms)
@@ -298,7 +340,7 @@ def main():
     e2e_total = 0.0
     for _ in range(e2e_steps):
         xh.copy_(xh_src)
-        flush.zero_()
+        flush_l2()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         e2e_step()
@@ -347,7 +389,7 @@ def main():
         stage_achieved = stage_bytes / (part_avg_ms * 1e-3) / 1e9
         line = dict(base)
         line["config"] = dict(base["config"],
-                              l2="flushed between steps (256 MiB memset outside the per-step events)",
+                              l2="flushed between steps outside the per-step events: 256 MiB memset, then a 256 MiB read so that no dirty lines are left",
                               timing="sum of per-step CUDA-event intervals, max over ranks",
                               kernel_path=args.path,
                               accumulate_pass="block-sparse (rows below fp32 resolution skipped)" if args.sparse
@@ -369,6 +411,8 @@ def main():
                          "share_of_stage": dom_ms / part_avg_ms,
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "kernels_ms": {k: round(v, 5) for k, v in kernel_avg.items()},
+                         "kernel_timing": "library CUDA events around each kernel, stage replayed from a CUDA graph"
+                         if stage_graph is not None else "library CUDA events around each kernel, eager launches",
                          "stage": {"what": "sdn_repel_partial: every kernel of the bank-streaming stage, against "
                                            "ONE pass over the bank (N*D*4 + N*4 + 2*Q*D*4 bytes)",
                                    "algorithmic_bytes": stage_bytes, "avg_ms": part_avg_ms, "min_ms": part_ms[0],

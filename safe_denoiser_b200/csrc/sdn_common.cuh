@@ -37,10 +37,19 @@ struct Prof {
     ProfSlot& s = slot[n];
     if (!s.e0) { cudaEventCreate(&s.e0); cudaEventCreate(&s.e1); }
     s.name = name;
-    cudaEventRecord(s.e0, st);
+    record(s.e0, st);
     return n++;
   }
-  void end(int id, cudaStream_t st) { if (id >= 0) cudaEventRecord(slot[id].e1, st); }
+  void end(int id, cudaStream_t st) { if (id >= 0) record(slot[id].e1, st); }
+  // inside a stream capture the record must become an EXTERNAL event node, otherwise the event cannot be
+  // synchronised / timed after the graph is replayed
+  static void record(cudaEvent_t e, cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+      cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+    else
+      cudaEventRecord(e, st);
+  }
 };
 extern Prof g_prof;
 
