@@ -264,7 +264,7 @@ def main():
     p0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     p1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     x.copy_(x_src)
-    if args.path in (0, 3, 4) and Q > 8 and D % 128 == 0:
+    if args.path in (0, 3, 4) and (Q > 8 or (Q > 4 and bank.N >= 1024)) and D % 128 == 0:
         bank.ensure_planes()
     kernel_ms = {}
     nv.profile_enable(True)

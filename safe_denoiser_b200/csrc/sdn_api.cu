@@ -13,9 +13,13 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static size_t generic_workspace_bytes(int64_t Q, int64_t N) { return align_up(sizeof(float) * Q * N, 256); }
 
+// Batched calls go to the tensor cores.  The one-pass CUDA-core kernel is FMA-bound from Q = 5 on (its Q = 5..8
+// instance runs at ~25 % of the HBM roofline), so for a bank of >= 1024 rows the two-phase tcgen05 path wins there too.
+static bool batched(int64_t Q, int64_t N) { return Q > 8 || (Q > 4 && N >= 1024); }
+
 static int pick_path(int32_t path, int64_t Q, int64_t N, int64_t D, const void* planes) {
   if (path == SDN_PATH_AUTO) {
-    if (umma_supported(Q, N, D, planes) && Q > 8) return SDN_PATH_UMMA;
+    if (umma_supported(Q, N, D, planes) && batched(Q, N)) return SDN_PATH_UMMA;
     if (stream_supported(Q, N, D)) return SDN_PATH_STREAM;
     return SDN_PATH_GENERIC;
   }
@@ -147,7 +151,7 @@ int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* p
     return SDN_E_ALIGN;
   g_prof.reset();
   cudaStream_t st = (cudaStream_t)stream;
-  if (Q > 8 && planes && z_out && umma_supported(Q, N, D, planes)) {
+  if (batched(Q, N) && planes && z_out && umma_supported(Q, N, D, planes)) {
     if (!workspace || workspace_bytes < umma_workspace_bytes(Q, N, D)) return SDN_E_WORKSPACE;
     return umma_conditioning(planes, sqnorm, N, D, x0_inout, Q, inv_two_sigma_sq, dist_power, bank_alpha, eps, scale,
                              gate_threshold, flags, num_out, z_out, neg_out, denom_out, gate_out, mean_out, k_out,

@@ -171,6 +171,10 @@ class Projector:
             s.xq = torch.empty(Q, self.bank.D, dtype=torch.float32, device=self.bank.device)
         return s
 
+    def _batched(self, Q: int) -> bool:
+        """Same rule as the library's AUTO dispatch: tensor-core path for Q > 8, and from Q = 5 on large banks."""
+        return Q > 8 or (Q > 4 and self.bank.N >= 1024)
+
     def _flat_query(self, x: torch.Tensor):
         if x.dtype != torch.float32 or not x.is_cuda:
             raise RuntimeError("query must be a CUDA fp32 tensor")
@@ -192,7 +196,8 @@ class Projector:
         L = nv.lib()
         st = nv.current_stream()
         Q, xf = self._flat_query(x0)
-        if Q > 8 and self.path in (nv.PATH_AUTO, nv.PATH_UMMA, nv.PATH_UMMA_BF16) and self.bank.D % 128 == 0:
+        if ((self._batched(Q) and self.path == nv.PATH_AUTO) or self.path in (nv.PATH_UMMA, nv.PATH_UMMA_BF16)) \
+                and self.bank.D % 128 == 0:
             self.bank.ensure_planes()        # batched calls go to the tcgen05 kernels
         s = self._get(Q, normalize_channels > 0)
         mo = None
@@ -235,17 +240,18 @@ class Projector:
         holds denom [Q], gate [Q] (int32), mean [1] and num [Q,D] as device tensors."""
         Q, xf = self._flat_query(x0)
         if (self.group is None and apply and normalize_channels == 0
-                and self.path in (nv.PATH_AUTO, nv.PATH_STREAM if Q <= 8 else nv.PATH_UMMA)
+                and self.path in (nv.PATH_AUTO, nv.PATH_UMMA if self._batched(Q) else nv.PATH_STREAM)
                 and self._few_launch.get(Q, True)):
             # one GPU, plain query: the fused sequences (2 launches for Q <= 8, 5 for batched) instead of 6-8
             b = self.bank
-            if Q > 8 and b.D % 128 == 0:
+            use_planes = (self._batched(Q) or self.path == nv.PATH_UMMA) and b.D % 128 == 0
+            if use_planes:
                 b.ensure_planes()
             s = self._get(Q, False)
             neg = torch.empty_like(xf) if want_neg else None
             flags = nv.EPI_GATE if gate_threshold is not None else 0
             rc = nv.lib().sdn_conditioning_fused(
-                nv.ptr(b.flat), nv.ptr(b.sqnorm), nv.ptr(b.planes) if Q > 8 else None, b.N, b.D, nv.ptr(xf), Q,
+                nv.ptr(b.flat), nv.ptr(b.sqnorm), nv.ptr(b.planes) if use_planes else None, b.N, b.D, nv.ptr(xf), Q,
                 1.0 / (2.0 * float(sigma) ** 2), int(dist_power), float(bank_alpha), float(eps), float(scale),
                 float(gate_threshold if gate_threshold is not None else 0.0), flags,
                 nv.ptr(s.num) if want_num else None, nv.ptr(s.z), nv.ptr(neg), nv.ptr(s.denom), nv.ptr(s.gate),

@@ -259,8 +259,10 @@ def test_shard_additivity_full_size(nv):
         s = Projector(NegativeBank(bank4[lo:hi])).partial_sums(x, 3.15)
         acc_n += s.num
         acc_z += s.z
-    assert rel(acc_n, num) <= 1e-5
-    assert rel(acc_z, z) <= 1e-5
+    # the full bank (Q = 8, N = 3000) runs on the tcgen05 kernels, the 375-row shards on the one-pass CUDA-core
+    # kernel: two arithmetic paths, so the bound is their joint error, not fp32 summation order alone
+    assert rel(acc_n, num) <= 1e-4
+    assert rel(acc_z, z) <= 1e-4
 
 
 def test_duplicated_bank_keeps_negative_mean(nv):

@@ -220,6 +220,9 @@ def test_new_entry_points_validate_arguments(nv):
     assert L.sdn_set_option(12345, 1) == -4
     assert L.sdn_repel_path(1, 515, 16384, 0, nv.PATH_AUTO) == nv.PATH_STREAM
     assert L.sdn_repel_path(64, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_UMMA
+    assert L.sdn_repel_path(8, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_UMMA         # FMA-bound for the cluster kernel
+    assert L.sdn_repel_path(8, 515, 16384, 1, nv.PATH_AUTO) == nv.PATH_STREAM
+    assert L.sdn_repel_path(4, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_STREAM
     assert L.sdn_repel_path(64, 3000, 16384, 0, nv.PATH_AUTO) == nv.PATH_GENERIC     # no planes: CUDA cores
     assert L.sdn_repel_path(3, 37, 256, 0, nv.PATH_AUTO) == nv.PATH_GENERIC          # D too small for the cluster kernel
     assert L.sdn_conditioning_fused(None, None, None, 1, 4, None, 1, 1.0, 1, 1.0, 0.0, 0.0, 0.0, 0,
