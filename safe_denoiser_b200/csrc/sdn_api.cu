@@ -193,6 +193,7 @@ struct HostCache {
   std::mutex mu;
   void* dev = nullptr;
   size_t dev_bytes = 0;
+  int device = -1;      // the device `dev` was allocated on
 } g_host;
 }  // namespace
 
@@ -216,12 +217,15 @@ int sdn_conditioning_host(const float* bank, const float* sqnorm, const void* pl
   const size_t ws = align_up(sdn_repel_workspace_bytes(Q, N, D, path), 256);
   // layout: x0 | xq | num | xsq | z | denom | workspace
   const size_t need = 3 * qd + 3 * qv + ws;
-  if (need > g_host.dev_bytes) {
+  int cur_dev = 0;
+  SDN_CUDA_OK(cudaGetDevice(&cur_dev));
+  if (need > g_host.dev_bytes || cur_dev != g_host.device) {
     if (g_host.dev) SDN_CUDA_OK(cudaFree(g_host.dev));
     g_host.dev = nullptr;
     g_host.dev_bytes = 0;
     SDN_CUDA_OK(cudaMalloc(&g_host.dev, need));
     g_host.dev_bytes = need;
+    g_host.device = cur_dev;
   }
   char* p = static_cast<char*>(g_host.dev);
   float* x0 = reinterpret_cast<float*>(p);

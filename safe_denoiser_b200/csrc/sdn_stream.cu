@@ -496,11 +496,13 @@ template <int Q, int VPT, int TN>
 static int launch_stream_t(const StreamArgs& a, int cs, int max_clusters_hint, int* ncl_out, cudaStream_t st) {
   auto kern = k_stream<Q, VPT, TN>;
   constexpr size_t smem = stream_smem_bytes<Q, VPT, TN>();
-  static bool configured = false;
-  static int max_clusters_by_cs[kStMaxCluster + 1] = {0};
-  if (!configured) {
+  static std::atomic<bool> configured[kMaxDevices];
+  static std::atomic<int> max_clusters_of[kMaxDevices][kStMaxCluster + 1];
+  const int dev = device_slot();
+  std::atomic<int>* max_clusters_by_cs = max_clusters_of[dev];
+  if (!configured[dev].load(std::memory_order_acquire)) {
     SDN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   if (max_clusters_by_cs[cs] == 0) {
     cudaLaunchConfig_t probe{};

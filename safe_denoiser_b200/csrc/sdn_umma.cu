@@ -954,12 +954,13 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   const UmmaLayout L = umma_layout(N, D);
   if (!ws || ws_bytes < L.total) return SDN_E_WORKSPACE;
   if (!load_encode()) return SDN_E_DEVICE;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<bool> configured[kMaxDevices];
+  const int dev = device_slot();
+  if (!configured[dev].load(std::memory_order_acquire)) {
     SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
     SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
     SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
-    configured = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   char* w = static_cast<char*>(ws);
   __nv_bfloat16* xpl = reinterpret_cast<__nv_bfloat16*>(w + L.off_x);
