@@ -214,10 +214,24 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int nkb = kb1 - kb0;
   const int nchunks = (nkb + kUChunk - 1) / kUChunk;
 
+  auto load_stage = [&](int i) {
+    const int s = i % kUStages;
+    uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
+    u_mbar_expect_tx(&sm.full[s], use_lo ? kStageBytes : 2 * kTileBytes);
+    const int kc = (kb0 + i) * kUK;
+    u_tma_2d(st, &tm_x, kc, 0, &sm.full[s]);
+    u_tma_2d(st + kTileBytes, &tm_hi, kc, row0, &sm.full[s]);
+    if (use_lo) u_tma_2d(st + 2 * kTileBytes, &tm_lo, kc, row0, &sm.full[s]);
+  };
+  const int npre = min(nkb, kUStages);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kUStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the first stages need nothing but this thread's own barriers: their HBM latency overlaps the TMEM
+    // allocation and the start-up barrier (the kernel is fill/drain bound at N ~ 3000)
+    u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
+    for (int i = 0; i < npre; ++i) load_stage(i);
   }
   if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kUBankTile);
   u_fence_before();
@@ -227,16 +241,9 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 
   if (warp == 0) {
     if (lane == 0) {
-      u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % kUStages;
-        if (i >= kUStages) u_mbar_wait(&sm.empty[s], (uint32_t)(((i / kUStages) + 1) & 1));
-        uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
-        u_mbar_expect_tx(&sm.full[s], use_lo ? kStageBytes : 2 * kTileBytes);
-        const int kc = (kb0 + i) * kUK;
-        u_tma_2d(st, &tm_x, kc, 0, &sm.full[s]);
-        u_tma_2d(st + kTileBytes, &tm_hi, kc, row0, &sm.full[s]);
-        if (use_lo) u_tma_2d(st + 2 * kTileBytes, &tm_lo, kc, row0, &sm.full[s]);
+      for (int i = npre; i < nkb; ++i) {
+        u_mbar_wait(&sm.empty[i % kUStages], (uint32_t)(((i / kUStages) + 1) & 1));
+        load_stage(i);
       }
     }
   } else if (warp == 1) {
@@ -556,10 +563,33 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   const int dblocks = (int)(D / kUDBlock);
   const int ntasks = (dblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+  // stage `it` <- row block i of this split, d-block task t
+  auto load_stage = [&](int it, int i, int t) {
+    const int d0 = ((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock;
+    const int s = it % kUStages;
+    uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
+    u_mbar_expect_tx(&sm.full[s], use_lo ? kStageBytes : 2 * kTileBytes);
+    const int rc = (rb0 + i) * kUK;                   // first bank row of this block
+    // P tile: two boxes of [64 rows][64 stacked q] (hi parts, lo parts), 8 KiB apart
+    u_tma_2d(st, &tm_p, 0, rc, &sm.full[s]);
+    u_tma_2d(st + 8192, &tm_p, 64, rc, &sm.full[s]);
+    // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart
+    u_tma_2d(st + kTileBytes, &tm_hi, d0, rc, &sm.full[s]);
+    u_tma_2d(st + kTileBytes + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
+    if (use_lo) {
+      u_tma_2d(st + 2 * kTileBytes, &tm_lo, d0, rc, &sm.full[s]);
+      u_tma_2d(st + 2 * kTileBytes + 8192, &tm_lo, d0 + 64, rc, &sm.full[s]);
+    }
+  };
+  // dense pass: the first stages depend on nothing but this thread's own barriers, so their latency overlaps
+  // the TMEM allocation and the start-up barrier
+  const int npre = (rowflags == nullptr && nrb > 0) ? min(ntasks * nrb, kUStages) : 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kUStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
+    for (int it = 0; it < npre; ++it) load_stage(it, it % nrb, it / nrb);
   }
   if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kUStack);
   if (warp == 0) {
@@ -588,26 +618,10 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {
-      u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
-      for (int it = 0; it < ntasks * nact; ++it) {
+      for (int it = npre; it < ntasks * nact; ++it) {
         const int t = it / nact, j = it - t * nact;
-        const int i = dense ? j : (int)act[j];
-        const int d0 = ((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock;
-        const int s = it % kUStages;
-        if (it >= kUStages) u_mbar_wait(&sm.empty[s], (uint32_t)(((it / kUStages) + 1) & 1));
-        uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
-        u_mbar_expect_tx(&sm.full[s], use_lo ? kStageBytes : 2 * kTileBytes);
-        const int rc = (rb0 + i) * kUK;                   // first bank row of this block
-        // P tile: two boxes of [64 rows][64 stacked q] (hi parts, lo parts), 8 KiB apart
-        u_tma_2d(st, &tm_p, 0, rc, &sm.full[s]);
-        u_tma_2d(st + 8192, &tm_p, 64, rc, &sm.full[s]);
-        // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart
-        u_tma_2d(st + kTileBytes, &tm_hi, d0, rc, &sm.full[s]);
-        u_tma_2d(st + kTileBytes + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
-        if (use_lo) {
-          u_tma_2d(st + 2 * kTileBytes, &tm_lo, d0, rc, &sm.full[s]);
-          u_tma_2d(st + 2 * kTileBytes + 8192, &tm_lo, d0 + 64, rc, &sm.full[s]);
-        }
+        if (it >= kUStages) u_mbar_wait(&sm.empty[it % kUStages], (uint32_t)(((it / kUStages) + 1) & 1));
+        load_stage(it, dense ? j : (int)act[j], t);
       }
     }
   } else if (warp == 1) {
