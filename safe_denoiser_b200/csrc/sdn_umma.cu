@@ -31,11 +31,25 @@ constexpr int kUStack = 128;     // stacked query rows: [0,64) hi parts, [64,128
 constexpr int kUQ = 64;          // max query rows per launch
 constexpr int kUBankTile = 128;  // bank rows per phase-A tile (MMA N)
 constexpr int kUDBlock = 128;    // d per phase-B CTA (MMA M)
-constexpr int kUStages = 4;
-constexpr int kUThreads = 192;
+constexpr int kUMaxStages = 4;
 constexpr uint32_t kTileBytes = 128 * 128;   // a [128 rows][64 bf16] tile = 16 KiB
-constexpr uint32_t kStageBytes = 3 * kTileBytes;
-constexpr size_t kUSmemBytes = kUStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kPipeBytes = 12 * kTileBytes;   // 192 KiB of pipeline stages, however they are cut
+constexpr size_t kUSmemBytes = kPipeBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+// One pass serves G groups of 64 query rows (G = 2 when a call brings more than 64): the bank tile of a stage is
+// shared by the groups, so 65..128 query rows cost one read of the bank per phase instead of two.  A stage holds
+// G query-side tiles (X planes in phase A, weight planes in phase B) + the hi and lo bank tiles; every group has
+// its own TMEM accumulator pair and its own four epilogue warps.
+template <int G>
+struct UCfg {
+  static constexpr int kStages = G == 1 ? 4 : 3;                       // 4 x 48 KiB or 3 x 64 KiB
+  static constexpr uint32_t kStageBytes = (uint32_t)(G + 2) * kTileBytes;
+  static constexpr uint32_t kHiOff = (uint32_t)G * kTileBytes;         // bank hi tile within a stage
+  static constexpr uint32_t kLoOff = (uint32_t)(G + 1) * kTileBytes;   // bank lo tile
+  static constexpr int kThreads = 64 + 128 * G;                        // TMA warp, MMA warp, 4 G epilogue warps
+  static constexpr uint32_t kAccCols = (uint32_t)G * 128;              // TMEM columns of one accumulator buffer
+  static_assert(kStages * kStageBytes == kPipeBytes, "stages must fill the pipeline area");
+};
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,7 +132,7 @@ __host__ __device__ constexpr uint32_t u_idesc(int M, int N, int a_mn_major, int
 }
 
 struct USmem {
-  uint8_t* tiles;       // [stages][3][16 KiB], 1024-byte aligned
+  uint8_t* tiles;       // [stages][G + 2][16 KiB], 1024-byte aligned
   uint64_t* full;       // [stages]
   uint64_t* empty;      // [stages]
   uint64_t* acc_full;   // [2]
@@ -129,9 +143,9 @@ __device__ __forceinline__ USmem u_carve(unsigned char* raw) {
   USmem s;
   const uintptr_t a = (reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023;
   s.tiles = reinterpret_cast<uint8_t*>(a);
-  s.full = reinterpret_cast<uint64_t*>(s.tiles + (size_t)kUStages * kStageBytes);
-  s.empty = s.full + kUStages;
-  s.acc_full = s.empty + kUStages;
+  s.full = reinterpret_cast<uint64_t*>(s.tiles + kPipeBytes);
+  s.empty = s.full + kUMaxStages;
+  s.acc_full = s.empty + kUMaxStages;
   s.acc_empty = s.acc_full + 2;
   s.tmem_base = reinterpret_cast<uint32_t*>(s.acc_empty + 2);
   return s;
@@ -193,7 +207,8 @@ k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------------ phase A
-// grid (row tiles, k splits).  S_T [ksplit][Npad][128] fp32: S_T[s][i][r] = sum over split s of X[r][d] * bank[i][d].
+// grid (row tiles, k splits).  S_T [G][ksplit][Npad][128] fp32:
+//   S_T[g][s][i][r] = sum over K split s of X_g[r][d] * bank[i][d]      (r = stacked query row of group g).
 //
 // The tensor core adds into its fp32 accumulator with truncation, and near a negative the distance is the
 // small difference of large dot products, so long accumulation chains cost accuracy (measured: 43 K-blocks in
@@ -201,10 +216,12 @@ k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
 // kUChunk K-blocks and the epilogue warps drain the finished one into fp32 registers (round-to-nearest adds).
 constexpr int kUChunk = 4;
 
-__global__ void __launch_bounds__(kUThreads, 1)
+template <int G>
+__global__ void __launch_bounds__(UCfg<G>::kThreads, 1)
 k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
             const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int64_t split_stride,
-            int kblocks_total, int ksplit, int use_lo) {
+            int64_t group_stride, int kblocks_total, int ksplit, int use_lo) {
+  using C = UCfg<G>;
   extern __shared__ unsigned char smem_raw[];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,25 +232,26 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int nchunks = (nkb + kUChunk - 1) / kUChunk;
 
   auto load_stage = [&](int i) {
-    const int s = i % kUStages;
-    uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
-    u_mbar_expect_tx(&sm.full[s], use_lo ? kStageBytes : 2 * kTileBytes);
+    const int s = i % C::kStages;
+    uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
+    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     const int kc = (kb0 + i) * kUK;
-    u_tma_2d(st, &tm_x, kc, 0, &sm.full[s]);
-    u_tma_2d(st + kTileBytes, &tm_hi, kc, row0, &sm.full[s]);
-    if (use_lo) u_tma_2d(st + 2 * kTileBytes, &tm_lo, kc, row0, &sm.full[s]);
+#pragma unroll
+    for (int g = 0; g < G; ++g) u_tma_2d(st + (size_t)g * kTileBytes, &tm_x, kc, g * kUStack, &sm.full[s]);
+    u_tma_2d(st + C::kHiOff, &tm_hi, kc, row0, &sm.full[s]);
+    if (use_lo) u_tma_2d(st + C::kLoOff, &tm_lo, kc, row0, &sm.full[s]);
   };
-  const int npre = min(nkb, kUStages);
+  const int npre = min(nkb, C::kStages);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kUStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
+    for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4 * G); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the first stages need nothing but this thread's own barriers: their HBM latency overlaps the TMEM
     // allocation and the start-up barrier (the kernel is fill/drain bound at N ~ 3000)
     u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
     for (int i = 0; i < npre; ++i) load_stage(i);
   }
-  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kUBankTile);
+  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * C::kAccCols);
   u_fence_before();
   __syncthreads();
   u_fence_after();
@@ -242,7 +260,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   if (warp == 0) {
     if (lane == 0) {
       for (int i = npre; i < nkb; ++i) {
-        u_mbar_wait(&sm.empty[i % kUStages], (uint32_t)(((i / kUStages) + 1) & 1));
+        u_mbar_wait(&sm.empty[i % C::kStages], (uint32_t)(((i / C::kStages) + 1) & 1));
         load_stage(i);
       }
     }
@@ -255,20 +273,23 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((c >> 1) + 1) & 1));
           u_fence_after();
         }
-        const uint32_t acc = tmem + (uint32_t)(buf * kUBankTile);
+        const uint32_t acc = tmem + (uint32_t)buf * C::kAccCols;
         const int i1 = min(nkb, (c + 1) * kUChunk);
         for (int i = c * kUChunk; i < i1; ++i) {
-          const int s = i % kUStages;
-          u_mbar_wait(&sm.full[s], (uint32_t)((i / kUStages) & 1));
+          const int s = i % C::kStages;
+          u_mbar_wait(&sm.full[s], (uint32_t)((i / C::kStages) & 1));
           u_fence_after();
-          const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
+          const uint32_t base = u_smem(sm.tiles + (size_t)s * C::kStageBytes);
 #pragma unroll
           for (int kk = 0; kk < kUK / 16; ++kk) {
-            const uint64_t a = u_desc(base + kk * 32, 16, 1024);
-            const uint64_t bh = u_desc(base + kTileBytes + kk * 32, 16, 1024);
-            const uint64_t bl = u_desc(base + 2 * kTileBytes + kk * 32, 16, 1024);
-            u_mma(acc, a, bh, idesc, (i > c * kUChunk || kk > 0) ? 1u : 0u);
-            if (use_lo) u_mma(acc, a, bl, idesc, 1u);
+            const uint64_t bh = u_desc(base + C::kHiOff + kk * 32, 16, 1024);
+            const uint64_t bl = u_desc(base + C::kLoOff + kk * 32, 16, 1024);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const uint64_t a = u_desc(base + (uint32_t)g * kTileBytes + kk * 32, 16, 1024);
+              u_mma(acc + (uint32_t)g * kUBankTile, a, bh, idesc, (i > c * kUChunk || kk > 0) ? 1u : 0u);
+              if (use_lo) u_mma(acc + (uint32_t)g * kUBankTile, a, bl, idesc, 1u);
+            }
           }
           u_commit(&sm.empty[s]);
         }
@@ -276,8 +297,10 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       }
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); lane index = stacked query row
+    // epilogue: warps 2..5 drain group 0, warps 6..9 group 1; a warp may touch TMEM lanes [32*(w%4), +32);
+    // lane index = stacked query row
     const int lq = warp & 3;
+    const int g = (warp - 2) >> 2;
     float sum[kUBankTile];
 #pragma unroll
     for (int j = 0; j < kUBankTile; ++j) sum[j] = 0.f;
@@ -285,7 +308,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const int buf = c & 1;
       u_mbar_wait(&sm.acc_full[buf], (uint32_t)((c >> 1) & 1));
       u_fence_after();
-      const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kUBankTile);
+      const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)buf * C::kAccCols + (uint32_t)(g * kUBankTile);
 #pragma unroll
       for (int cc = 0; cc < kUBankTile / 32; ++cc) {
         float v[32];
@@ -299,7 +322,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     // every K split owns its own partial buffer: plain coalesced stores, summed by k_umma_weights
     const int r = lq * 32 + lane;
-    float* dst = S_T + (int64_t)blockIdx.y * split_stride + (int64_t)row0 * kUStack + r;
+    float* dst = S_T + (int64_t)g * group_stride + (int64_t)blockIdx.y * split_stride + (int64_t)row0 * kUStack + r;
 #pragma unroll
     for (int j = 0; j < kUBankTile; ++j) dst[(int64_t)j * kUStack] = sum[j];
   }
@@ -307,7 +330,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   __syncthreads();
   if (warp == 1) {
     u_fence_after();
-    u_tmem_dealloc(tmem, 2 * kUBankTile);
+    u_tmem_dealloc(tmem, 2 * C::kAccCols);
   }
 }
 
@@ -532,19 +555,22 @@ constexpr int kBChunk = 64;        // row blocks per TMEM accumulation chain in 
 constexpr int kMaxActive = 4096;   // row blocks a CTA can index in its active list (N <= 262144 per split)
 
 // Optional correction fused into phase B's epilogue (one GPU, no bank-row split): x0 -= scale * num / (z + eps).
+// Pointers address query row 0 of the pass; group g of the pass uses rows [64 g, 64 g + 64).
 struct AccumEpi {
   const float* z;       // null: no fused correction
   float eps, scale, gate_thr; int flags;
   float* x0; float* neg_out; float* denom_out; int32_t* gate_out; float* mean_out; float inv_qd;
 };
 
-// grid (D / 128, n splits).  num[q][d] (+)= sum_i P[q][i] * (hi+lo)[i][d] over this split's bank rows.
-template <bool CHUNKED>
-__global__ void __launch_bounds__(kUThreads, 1)
+// grid (D / 128, n splits).  num[q][d] (+)= sum_i P[q][i] * (hi+lo)[i][d] over this split's bank rows, for the
+// Q <= 64 G query rows of the pass; the weight planes of group g are rows [g * p_group_rows, +Npad) of tm_p.
+template <bool CHUNKED, int G>
+__global__ void __launch_bounds__(UCfg<G>::kThreads, 1)
 k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
              const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
-             int rblocks_total, int nsplit, int use_atomic, int use_lo, const int* rowflags,
+             int rblocks_total, int nsplit, int use_atomic, int use_lo, int p_group_rows, const int* rowflags,
              const int* __restrict__ list_count, const int* __restrict__ dense_flag, const AccumEpi epi) {
+  using C = UCfg<G>;
   if (dense_flag && __ldg(dense_flag)) {
     rowflags = nullptr;                                          // flat regime: no flags were built
   } else if (list_count && siglist_all_short(list_count, Q)) {
@@ -566,32 +592,35 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   // stage `it` <- row block i of this split, d-block task t
   auto load_stage = [&](int it, int i, int t) {
     const int d0 = ((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock;
-    const int s = it % kUStages;
-    uint8_t* st = sm.tiles + (size_t)s * kStageBytes;
-    u_mbar_expect_tx(&sm.full[s], use_lo ? kStageBytes : 2 * kTileBytes);
+    const int s = it % C::kStages;
+    uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
+    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     const int rc = (rb0 + i) * kUK;                   // first bank row of this block
-    // P tile: two boxes of [64 rows][64 stacked q] (hi parts, lo parts), 8 KiB apart
-    u_tma_2d(st, &tm_p, 0, rc, &sm.full[s]);
-    u_tma_2d(st + 8192, &tm_p, 64, rc, &sm.full[s]);
+    // P tiles: per group two boxes of [64 rows][64 stacked q] (hi parts, lo parts), 8 KiB apart
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      u_tma_2d(st + (size_t)g * kTileBytes, &tm_p, 0, g * p_group_rows + rc, &sm.full[s]);
+      u_tma_2d(st + (size_t)g * kTileBytes + 8192, &tm_p, 64, g * p_group_rows + rc, &sm.full[s]);
+    }
     // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart
-    u_tma_2d(st + kTileBytes, &tm_hi, d0, rc, &sm.full[s]);
-    u_tma_2d(st + kTileBytes + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
+    u_tma_2d(st + C::kHiOff, &tm_hi, d0, rc, &sm.full[s]);
+    u_tma_2d(st + C::kHiOff + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
     if (use_lo) {
-      u_tma_2d(st + 2 * kTileBytes, &tm_lo, d0, rc, &sm.full[s]);
-      u_tma_2d(st + 2 * kTileBytes + 8192, &tm_lo, d0 + 64, rc, &sm.full[s]);
+      u_tma_2d(st + C::kLoOff, &tm_lo, d0, rc, &sm.full[s]);
+      u_tma_2d(st + C::kLoOff + 8192, &tm_lo, d0 + 64, rc, &sm.full[s]);
     }
   };
   // dense pass: the first stages depend on nothing but this thread's own barriers, so their latency overlaps
   // the TMEM allocation and the start-up barrier
-  const int npre = (rowflags == nullptr && nrb > 0) ? min(ntasks * nrb, kUStages) : 0;
+  const int npre = (rowflags == nullptr && nrb > 0) ? min(ntasks * nrb, C::kStages) : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kUStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
+    for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4 * G); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
     for (int it = 0; it < npre; ++it) load_stage(it, it % nrb, it / nrb);
   }
-  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kUStack);
+  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * C::kAccCols);
   if (warp == 0) {
     // compact the list of row blocks that hold a non-negligible weight (dense when no flags are given)
     int cnt = 0;
@@ -620,7 +649,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     if (lane == 0) {
       for (int it = npre; it < ntasks * nact; ++it) {
         const int t = it / nact, j = it - t * nact;
-        if (it >= kUStages) u_mbar_wait(&sm.empty[it % kUStages], (uint32_t)(((it / kUStages) + 1) & 1));
+        if (it >= C::kStages) u_mbar_wait(&sm.empty[it % C::kStages], (uint32_t)(((it / C::kStages) + 1) & 1));
         load_stage(it, dense ? j : (int)act[j], t);
       }
     }
@@ -628,69 +657,69 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     if (lane == 0) {
       constexpr uint32_t id_full = u_idesc(kUDBlock, kUStack, 1, 1);   // hi * [P_hi | P_lo]
       constexpr uint32_t id_half = u_idesc(kUDBlock, kUQ, 1, 1);       // lo * P_hi
+      // one stage = one block of 64 bank rows: 4 K-steps x G groups x (hi, lo) MMAs
+      auto mma_stage = [&](int it, uint32_t acc, bool first) {
+        const int s = it % C::kStages;
+        u_mbar_wait(&sm.full[s], (uint32_t)((it / C::kStages) & 1));
+        u_fence_after();
+        const uint32_t base = u_smem(sm.tiles + (size_t)s * C::kStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < kUK / 16; ++kk) {
+          const uint64_t ah = u_desc(base + C::kHiOff + kk * 2048, 8192, 1024);        // bank^T, MN-major
+          const uint64_t al = u_desc(base + C::kLoOff + kk * 2048, 8192, 1024);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const uint64_t b = u_desc(base + (uint32_t)g * kTileBytes + kk * 2048, 8192, 1024);   // P_g^T, MN-major
+            u_mma(acc + (uint32_t)g * kUStack, ah, b, id_full, (!first || kk > 0) ? 1u : 0u);
+            if (use_lo) u_mma(acc + (uint32_t)g * kUStack, al, b, id_half, 1u);
+          }
+        }
+        u_commit(&sm.empty[s]);
+      };
       if constexpr (!CHUNKED) {
-      for (int t = 0; t < ntasks && nact > 0; ++t) {
-        const int buf = t & 1;
-        if (t >= 2) {
-          u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((t >> 1) + 1) & 1));
-          u_fence_after();
-        }
-        const uint32_t acc = tmem + (uint32_t)(buf * kUStack);
-        for (int i = 0; i < nact; ++i) {
-          const int it = t * nact + i;
-          const int s = it % kUStages;
-          u_mbar_wait(&sm.full[s], (uint32_t)((it / kUStages) & 1));
-          u_fence_after();
-          const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
-#pragma unroll
-          for (int kk = 0; kk < kUK / 16; ++kk) {
-            const uint64_t b = u_desc(base + kk * 2048, 8192, 1024);                    // P^T, MN-major
-            const uint64_t ah = u_desc(base + kTileBytes + kk * 2048, 8192, 1024);      // bank^T, MN-major
-            const uint64_t al = u_desc(base + 2 * kTileBytes + kk * 2048, 8192, 1024);
-            u_mma(acc, ah, b, id_full, (i > 0 || kk > 0) ? 1u : 0u);
-            if (use_lo) u_mma(acc, al, b, id_half, 1u);
+        for (int t = 0; t < ntasks && nact > 0; ++t) {
+          const int buf = t & 1;
+          if (t >= 2) {
+            u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((t >> 1) + 1) & 1));
+            u_fence_after();
           }
-          u_commit(&sm.empty[s]);
+          const uint32_t acc = tmem + (uint32_t)buf * C::kAccCols;
+          for (int i = 0; i < nact; ++i) mma_stage(t * nact + i, acc, i == 0);
+          u_commit(&sm.acc_full[buf]);
         }
-        u_commit(&sm.acc_full[buf]);
-      }
       } else {
-      // unit u = (d-block task, chunk of kBChunk row blocks); consecutive units alternate TMEM accumulators so that
-      // no fp32 accumulation chain in the tensor core is longer than kBChunk * 8 MMAs (its adds truncate)
-      for (int u = 0; nact > 0 && u < ntasks * nchunks; ++u) {
-        const int t = u / nchunks, c = u - t * nchunks;
-        const int buf = u & 1;
-        if (u >= 2) {
-          u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((u >> 1) + 1) & 1));
-          u_fence_after();
-        }
-        const uint32_t acc = tmem + (uint32_t)(buf * kUStack);
-        const int j0 = c * kBChunk, j1 = min(nact, j0 + kBChunk);
-        for (int i = j0; i < j1; ++i) {
-          const int it = t * nact + i;
-          const int s = it % kUStages;
-          u_mbar_wait(&sm.full[s], (uint32_t)((it / kUStages) & 1));
-          u_fence_after();
-          const uint32_t base = u_smem(sm.tiles + (size_t)s * kStageBytes);
-#pragma unroll
-          for (int kk = 0; kk < kUK / 16; ++kk) {
-            const uint64_t b = u_desc(base + kk * 2048, 8192, 1024);                    // P^T, MN-major
-            const uint64_t ah = u_desc(base + kTileBytes + kk * 2048, 8192, 1024);      // bank^T, MN-major
-            const uint64_t al = u_desc(base + 2 * kTileBytes + kk * 2048, 8192, 1024);
-            u_mma(acc, ah, b, id_full, (i > j0 || kk > 0) ? 1u : 0u);
-            if (use_lo) u_mma(acc, al, b, id_half, 1u);
+        // unit u = (d-block task, chunk of kBChunk row blocks); consecutive units alternate TMEM accumulators so
+        // that no fp32 accumulation chain in the tensor core is longer than kBChunk * 8 MMAs (its adds truncate)
+        for (int u = 0; nact > 0 && u < ntasks * nchunks; ++u) {
+          const int t = u / nchunks, c = u - t * nchunks;
+          const int buf = u & 1;
+          if (u >= 2) {
+            u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((u >> 1) + 1) & 1));
+            u_fence_after();
           }
-          u_commit(&sm.empty[s]);
+          const uint32_t acc = tmem + (uint32_t)buf * C::kAccCols;
+          const int j0 = c * kBChunk, j1 = min(nact, j0 + kBChunk);
+          for (int i = j0; i < j1; ++i) mma_stage(t * nact + i, acc, i == j0);
+          u_commit(&sm.acc_full[buf]);
         }
-        u_commit(&sm.acc_full[buf]);
-      }
       }
     }
   } else {
+    // epilogue: warps 2..5 serve query group 0, warps 6..9 group 1
     const int lq = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int Qg = min(kUQ, Q - g * kUQ);                         // query rows of this group (>= 1)
+    const int64_t qoff = (int64_t)g * kUQ * D;
+    float* const numg = num ? num + qoff : nullptr;
+    const float* const zg = epi.z ? epi.z + g * kUQ : nullptr;
+    float* const x0g = epi.x0 ? epi.x0 + qoff : nullptr;
+    float* const negg = epi.neg_out ? epi.neg_out + qoff : nullptr;
+    float* const denomg = epi.denom_out ? epi.denom_out + g * kUQ : nullptr;
+    int32_t* const gateg = epi.gate_out ? epi.gate_out + g * kUQ : nullptr;
+    const uint32_t tcol = (uint32_t)(g * kUStack);
     float msum = 0.f;
     if constexpr (!CHUNKED) {
-    // epilogue: TMEM lane = d within the block, column = stacked query row
+    // TMEM lane = d within the block, column = stacked query row
 #pragma unroll 1
     for (int t = 0; t < ntasks; ++t) {
     const int buf = t & 1;
@@ -699,7 +728,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       u_fence_after();
     }
     const int64_t d = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock + lq * 32 + lane;
-    const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kUStack);
+    const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)buf * C::kAccCols + tcol;
 #pragma unroll 1
     for (int c = 0; c < kUQ / 32; ++c) {
       float a[32], b[32];
@@ -710,30 +739,30 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] = b[j] = 0.f;
       }
-      if (epi.z) {
+      if (zg) {
         // all loads of the chunk first: the stores below may alias them as far as the compiler knows, and one
         // load -> store round trip per query row costs ~25 us per launch
         float xv[32], dn[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int q = min(c * 32 + j, Q - 1);
-          dn[j] = __ldg(epi.z + q) + epi.eps;
-          xv[j] = epi.x0 ? __ldcg(epi.x0 + (int64_t)q * D + d) : 0.f;
+          const int q = min(c * 32 + j, Qg - 1);
+          dn[j] = __ldg(zg + q) + epi.eps;
+          xv[j] = x0g ? __ldcg(x0g + (int64_t)q * D + d) : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int q = c * 32 + j;
-          if (q < Q) {
+          if (q < Qg) {
             const float v = a[j] + b[j];
             const int64_t o = (int64_t)q * D + d;
             const float n = v / dn[j];
-            if (num) num[o] = v;
-            if (epi.neg_out) epi.neg_out[o] = n;
-            if (epi.x0) epi.x0[o] = fmaf(-epi.scale, n, xv[j]);
+            if (numg) numg[o] = v;
+            if (negg) negg[o] = n;
+            if (x0g) x0g[o] = fmaf(-epi.scale, n, xv[j]);
             msum += fminf(fmaxf(n, -1e10f), 1e10f);
             if (blockIdx.x == 0 && lq == 0 && lane == 0) {
-              if (epi.denom_out) epi.denom_out[q] = dn[j];
-              if (epi.gate_out) epi.gate_out[q] = (!(epi.flags & SDN_EPI_GATE) || dn[j] > epi.gate_thr) ? 1 : 0;
+              if (denomg) denomg[q] = dn[j];
+              if (gateg) gateg[q] = (!(epi.flags & SDN_EPI_GATE) || dn[j] > epi.gate_thr) ? 1 : 0;
             }
           }
         }
@@ -741,8 +770,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int q = c * 32 + j;
-          if (q < Q) {
-            float* o = num + (int64_t)q * D + d;
+          if (q < Qg) {
+            float* o = numg + (int64_t)q * D + d;
             if (use_atomic) atomicAdd(o, a[j] + b[j]); else *o = a[j] + b[j];
           }
         }
@@ -754,7 +783,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
     }   // tasks
     } else {
-    // epilogue: TMEM lane = d within the block, column = stacked query row; running fp32 sums over the chunks
+    // running fp32 sums over the chunks
     float sum[kUQ];
 #pragma unroll
     for (int j = 0; j < kUQ; ++j) sum[j] = 0.f;
@@ -767,7 +796,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       if (nact > 0) {
         u_mbar_wait(&sm.acc_full[buf], (uint32_t)((u >> 1) & 1));
         u_fence_after();
-        const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kUStack);
+        const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)buf * C::kAccCols + tcol;
 #pragma unroll
         for (int cq = 0; cq < kUQ / 32; ++cq) {
           float a[32], b[32];
@@ -784,30 +813,30 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       if (c != nchunks - 1 && nact > 0) continue;
       // ---- last chunk of this d-block: write it out
       const int64_t d = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock + lq * 32 + lane;
-      if (epi.z) {
+      if (zg) {
 #pragma unroll
         for (int cq = 0; cq < kUQ / 32; ++cq) {
           float xv[32], dn[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int q = min(cq * 32 + j, Q - 1);
-            dn[j] = __ldg(epi.z + q) + epi.eps;
-            xv[j] = epi.x0 ? __ldcg(epi.x0 + (int64_t)q * D + d) : 0.f;
+            const int q = min(cq * 32 + j, Qg - 1);
+            dn[j] = __ldg(zg + q) + epi.eps;
+            xv[j] = x0g ? __ldcg(x0g + (int64_t)q * D + d) : 0.f;
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int q = cq * 32 + j;
-            if (q < Q) {
+            if (q < Qg) {
               const float v = sum[cq * 32 + j];
               const int64_t o = (int64_t)q * D + d;
               const float n = v / dn[j];
-              if (num) num[o] = v;
-              if (epi.neg_out) epi.neg_out[o] = n;
-              if (epi.x0) epi.x0[o] = fmaf(-epi.scale, n, xv[j]);
+              if (numg) numg[o] = v;
+              if (negg) negg[o] = n;
+              if (x0g) x0g[o] = fmaf(-epi.scale, n, xv[j]);
               msum += fminf(fmaxf(n, -1e10f), 1e10f);
               if (blockIdx.x == 0 && lq == 0 && lane == 0) {
-                if (epi.denom_out) epi.denom_out[q] = dn[j];
-                if (epi.gate_out) epi.gate_out[q] = (!(epi.flags & SDN_EPI_GATE) || dn[j] > epi.gate_thr) ? 1 : 0;
+                if (denomg) denomg[q] = dn[j];
+                if (gateg) gateg[q] = (!(epi.flags & SDN_EPI_GATE) || dn[j] > epi.gate_thr) ? 1 : 0;
               }
             }
           }
@@ -815,8 +844,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       } else {
 #pragma unroll
         for (int j = 0; j < kUQ; ++j) {
-          if (j < Q) {
-            float* o = num + (int64_t)j * D + d;
+          if (j < Qg) {
+            float* o = numg + (int64_t)j * D + d;
             if (use_atomic) atomicAdd(o, sum[j]); else *o = sum[j];
           }
         }
@@ -825,7 +854,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       for (int j = 0; j < kUQ; ++j) sum[j] = 0.f;
     }   // units
     }
-    if (epi.z && epi.mean_out) {
+    if (zg && epi.mean_out) {
       msum = warp_sum(msum);
       if (lane == 0) atomicAdd(epi.mean_out, msum * epi.inv_qd);
     }
@@ -834,7 +863,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   __syncthreads();
   if (warp == 1) {
     u_fence_after();
-    u_tmem_dealloc(tmem, 2 * kUStack);
+    u_tmem_dealloc(tmem, 2 * C::kAccCols);
   }
 }
 
@@ -877,27 +906,39 @@ int umma_ksplit(int64_t npad, int64_t D) {
 }
 
 struct UmmaLayout {
+  int G;               // query groups of 64 rows per pass (1 or 2)
   int64_t npad;        // bank rows padded to 128
   int ksplit;
+  int nflags;          // row blocks of 64 bank rows
+  int xsq_nparts;
   size_t off_x, off_s, off_p, off_z, off_f, off_q, total;
+  // per-group strides (elements)
+  int64_t split_stride, group_stride_s, zpart_stride;
 };
-UmmaLayout umma_layout(int64_t N, int64_t D) {
+UmmaLayout umma_layout(int64_t Q, int64_t N, int64_t D) {
   UmmaLayout L;
+  L.G = Q > kUQ ? 2 : 1;
   L.npad = cdiv(N, 128) * 128;
   L.ksplit = umma_ksplit(L.npad, D);
+  L.nflags = (int)(L.npad / kUK);
+  L.xsq_nparts = (int)cdiv(D, 1024);
+  L.split_stride = L.npad * kUStack;
+  L.group_stride_s = (int64_t)L.ksplit * L.split_stride;
+  L.zpart_stride = (L.npad / kWRows) * kUStack + 64;
+  const size_t G = (size_t)L.G;
   size_t o = 0;
-  L.off_x = o; o += (size_t)kUStack * D * 2;                 // X planes
+  L.off_x = o; o += G * kUStack * D * 2;                     // X planes [G][128][D]
   o = (o + 255) / 256 * 256;
-  L.off_s = o; o += (size_t)L.ksplit * L.npad * kUStack * 4; // S^T, one partial per K split
+  L.off_s = o; o += G * L.group_stride_s * 4;                // S^T [G][ksplit][Npad][128], one partial per K split
   o = (o + 255) / 256 * 256;
-  L.off_p = o; o += (size_t)kUStack * L.npad * 2;            // P planes
+  L.off_p = o; o += G * kUStack * L.npad * 2;                // P planes [G][Npad][128]
   o = (o + 255) / 256 * 256;
-  L.off_z = o; o += (size_t)(L.npad / kWRows) * kUStack * 4 + 256;   // per-block z sums | maxima
+  L.off_z = o; o += G * L.zpart_stride * 4;                  // per-block z sums | maxima, per group
   o = (o + 255) / 256 * 256;
-  L.off_f = o; o += (size_t)(L.npad / kUK) * 4 + kUQ * 4 + kUQ * 4 + 16 + (size_t)kUQ * kListCap * 8 + 256;
-                                                       // row-block flags | kmax[64] | count[64] | rows | ks
+  // row-block flags | kmax[G 64] | count[G 64] | dense (4 words) | rows[G 64][cap] | ks[G 64][cap]
+  L.off_f = o; o += (size_t)L.nflags * 4 + G * kUQ * 4 + G * kUQ * 4 + 16 + G * kUQ * kListCap * 8 + 256;
   o = (o + 255) / 256 * 256;
-  L.off_q = o; o += (size_t)cdiv(D, 1024) * kUQ * 4;          // ||x||^2 partials of the fused query prepare
+  L.off_q = o; o += G * L.xsq_nparts * kUQ * 4;              // ||x||^2 partials of the fused query prepare
   L.total = (o + 255) / 256 * 256;
   return L;
 }
@@ -905,30 +946,30 @@ UmmaLayout umma_layout(int64_t N, int64_t D) {
 
 bool umma_supported(int64_t Q, int64_t N, int64_t D, const void* planes) {
   return planes != nullptr && Q >= 1 && N >= 1 && D >= kUDBlock && D % kUDBlock == 0 &&
-         N < (1ll << 31) && D < (1ll << 31);
+         N < (1ll << 30) && D < (1ll << 31);
 }
 
 size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D) {
   if (Q < 1 || D % kUDBlock) return 0;
-  return umma_layout(N, D).total;
+  return umma_layout(Q, N, D).total;
 }
 
-static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
-                           const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
-                           float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, const AccumEpi* epi,
-                           float* zero_word, bool bf16_bank);
+static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                     const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
+                     float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, const AccumEpi* epi,
+                     float* zero_word, bool bf16_bank);
 
-// More than 64 query rows: one two-phase pass over the bank per group of 64 (the TMEM accumulator of phase B
-// holds 128 d x 128 stacked query columns).
+// One two-phase pass over the bank serves up to 128 query rows (two groups of 64: the TMEM of an SM holds two
+// double-buffered 128 x 128 accumulators); more rows take ceil(Q / 128) passes.
 int umma_partial(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
                  const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
                  float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, bool bf16_bank) {
   if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
-  for (int64_t q0 = 0; q0 < Q; q0 += kUQ) {
-    const int64_t qn = std::min<int64_t>(kUQ, Q - q0);
-    const int rc = umma_partial_64(planes, sqnorm, N, D, xq + q0 * D, xsq ? xsq + q0 : nullptr, qn, inv2s2, power, alpha,
-                                   num ? num + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws,
-                                   ws_bytes, st, nullptr, nullptr, bf16_bank);
+  for (int64_t q0 = 0; q0 < Q; q0 += 2 * kUQ) {
+    const int64_t qn = std::min<int64_t>(2 * kUQ, Q - q0);
+    const int rc = umma_pass(planes, sqnorm, N, D, xq + q0 * D, xsq ? xsq + q0 : nullptr, qn, inv2s2, power, alpha,
+                             num ? num + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws, ws_bytes, st,
+                             nullptr, nullptr, bf16_bank);
     if (rc) return rc;
   }
   return SDN_OK;
@@ -946,34 +987,65 @@ int umma_conditioning(const void* planes, const float* sqnorm, int64_t N, int64_
     if (std::max(1, std::min(rblocks / 8, kNumSMs / dblocks)) != 1)
       return SDN_E_UNSUPPORTED;   // phase B would split the bank rows: the correction cannot be fused
   }
-  for (int64_t q0 = 0; q0 < Q; q0 += kUQ) {
-    const int64_t qn = std::min<int64_t>(kUQ, Q - q0);
+  for (int64_t q0 = 0; q0 < Q; q0 += 2 * kUQ) {
+    const int64_t qn = std::min<int64_t>(2 * kUQ, Q - q0);
     AccumEpi epi{};
     epi.z = z + q0; epi.eps = eps; epi.scale = scale; epi.gate_thr = gate_thr; epi.flags = flags;
     epi.x0 = x0_inout + q0 * D; epi.neg_out = neg_out ? neg_out + q0 * D : nullptr;
     epi.denom_out = denom_out ? denom_out + q0 : nullptr; epi.gate_out = gate_out ? gate_out + q0 : nullptr;
     epi.mean_out = mean_out; epi.inv_qd = 1.f / (float)(Q * D);
-    const int rc = umma_partial_64(planes, sqnorm, N, D, x0_inout + q0 * D, nullptr, qn, inv2s2, power, alpha,
-                                   num_out ? num_out + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws,
-                                   ws_bytes, st, &epi, q0 == 0 ? mean_out : nullptr, false);
+    const int rc = umma_pass(planes, sqnorm, N, D, x0_inout + q0 * D, nullptr, qn, inv2s2, power, alpha,
+                             num_out ? num_out + q0 * D : nullptr, z + q0, k_out ? k_out + q0 * N : nullptr, ws,
+                             ws_bytes, st, &epi, q0 == 0 ? mean_out : nullptr, false);
     if (rc) return rc;
   }
   return SDN_OK;
 }
 
-static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
-                           const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
-                           float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, const AccumEpi* epi,
-                           float* zero_word, bool bf16_bank) {
-  const UmmaLayout L = umma_layout(N, D);
+namespace {
+template <int G>
+int configure_kernels() {
+  SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_dots<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+  SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<false, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+  SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<true, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+  return SDN_OK;
+}
+
+struct AccumLaunch {
+  CUtensorMap tm_p, tm_hi, tm_lo;
+  float* num; int64_t D; int Q, rblocks, nsplit, use_atomic, use_lo, p_group_rows;
+  const int* flags; const int* count; const int* dense;
+  AccumEpi e;
+  int gridx; bool chunked;
+};
+template <int G>
+void launch_accum(const AccumLaunch& a, cudaStream_t st) {
+  const dim3 grid(a.gridx, a.nsplit);
+  if (a.chunked)
+    k_umma_accum<true, G><<<grid, UCfg<G>::kThreads, kUSmemBytes, st>>>(a.tm_p, a.tm_hi, a.tm_lo, a.num, a.D, a.Q, a.rblocks,
+                                                                      a.nsplit, a.use_atomic, a.use_lo, a.p_group_rows,
+                                                                      a.flags, a.count, a.dense, a.e);
+  else
+    k_umma_accum<false, G><<<grid, UCfg<G>::kThreads, kUSmemBytes, st>>>(a.tm_p, a.tm_hi, a.tm_lo, a.num, a.D, a.Q, a.rblocks,
+                                                                       a.nsplit, a.use_atomic, a.use_lo, a.p_group_rows,
+                                                                       a.flags, a.count, a.dense, a.e);
+}
+}  // namespace
+
+static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                     const float* xsq, int64_t Q, float inv2s2, int power, float alpha, float* num, float* z,
+                     float* k_out, void* ws, size_t ws_bytes, cudaStream_t st, const AccumEpi* epi,
+                     float* zero_word, bool bf16_bank) {
+  const UmmaLayout L = umma_layout(Q, N, D);
+  const int G = L.G;
   if (!ws || ws_bytes < L.total) return SDN_E_WORKSPACE;
   if (!load_encode()) return SDN_E_DEVICE;
   static std::atomic<bool> configured[kMaxDevices];
   const int dev = device_slot();
   if (!configured[dev].load(std::memory_order_acquire)) {
-    SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
-    SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
-    SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+    int rc;
+    if ((rc = configure_kernels<1>())) return rc;
+    if ((rc = configure_kernels<2>())) return rc;
     configured[dev].store(true, std::memory_order_release);
   }
   char* w = static_cast<char*>(ws);
@@ -983,76 +1055,96 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
   const __nv_bfloat16* hi = static_cast<const __nv_bfloat16*>(planes);
   const __nv_bfloat16* lo = hi + N * D;
 
-  // tensor maps depend only on (planes, workspace, N, D): re-encode when one of those changes
-  struct MapCache { const void* planes; const void* ws; int64_t N, D; CUtensorMap m[6]; bool valid; };
-  static MapCache cache{nullptr, nullptr, 0, 0, {}, false};
+  // tensor maps depend only on (planes, workspace, N, D, G): re-encode when one of those changes
+  struct MapCache { const void* planes; const void* ws; int64_t N, D; int G; CUtensorMap m[6]; bool valid; };
+  static MapCache cache{nullptr, nullptr, 0, 0, 0, {}, false};
   static std::mutex cache_mu;
   CUtensorMap tm_x, tm_hiA, tm_loA, tm_p, tm_hiB, tm_loB;
   {
     std::lock_guard<std::mutex> lk(cache_mu);
-    if (!(cache.valid && cache.planes == planes && cache.ws == ws && cache.N == N && cache.D == D)) {
+    if (!(cache.valid && cache.planes == planes && cache.ws == ws && cache.N == N && cache.D == D && cache.G == G)) {
       int rc;
       cache.valid = false;
-      if ((rc = make_map(&cache.m[0], xpl, kUStack, D, kUStack, kUK))) return rc;
+      if ((rc = make_map(&cache.m[0], xpl, (uint64_t)G * kUStack, D, kUStack, kUK))) return rc;
       if ((rc = make_map(&cache.m[1], hi, N, D, kUBankTile, kUK))) return rc;
       if ((rc = make_map(&cache.m[2], lo, N, D, kUBankTile, kUK))) return rc;
-      if ((rc = make_map(&cache.m[3], P, L.npad, kUStack, kUK, 64))) return rc;
+      if ((rc = make_map(&cache.m[3], P, (uint64_t)G * L.npad, kUStack, kUK, 64))) return rc;
       if ((rc = make_map(&cache.m[4], hi, N, D, kUK, 64))) return rc;
       if ((rc = make_map(&cache.m[5], lo, N, D, kUK, 64))) return rc;
-      cache.planes = planes; cache.ws = ws; cache.N = N; cache.D = D; cache.valid = true;
+      cache.planes = planes; cache.ws = ws; cache.N = N; cache.D = D; cache.G = G; cache.valid = true;
     }
     tm_x = cache.m[0]; tm_hiA = cache.m[1]; tm_loA = cache.m[2]; tm_p = cache.m[3]; tm_hiB = cache.m[4]; tm_loB = cache.m[5];
   }
 
-  // query planes
+  // significant-row lists, shared by the groups of the pass (flags and the dense mark are unions over the groups;
+  // counts, rows and weights are indexed by the query row within the pass)
+  const int nflags = L.nflags;
+  SigLists lists{};
+  lists.flags = reinterpret_cast<int*>(w + L.off_f);
+  float* kmax = reinterpret_cast<float*>(lists.flags + nflags);
+  lists.count = reinterpret_cast<int*>(kmax + G * kUQ);
+  lists.dense = lists.count + G * kUQ;
+  lists.rows = lists.dense + 4;
+  lists.ks = reinterpret_cast<float*>(lists.rows + G * kUQ * kListCap);
+  const bool sparse = g_skip_negligible.load(std::memory_order_relaxed) && nflags <= kMaxActive && (num || epi);
   float* zpart = reinterpret_cast<float*>(w + L.off_z);
   float* xsq_part = reinterpret_cast<float*>(w + L.off_q);
-  const int xsq_nparts = (int)cdiv(D, 1024);
+  auto group_rows = [&](int g) { return (int)std::min<int64_t>(kUQ, Q - (int64_t)g * kUQ); };
+
+  // query planes (one launch per group of 64 rows)
   int pid = g_prof.begin(xsq ? "k_umma_xprep" : "k_umma_qprep", st);
-  if (xsq) {
-    k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xq, (int)Q, D, xpl);
-  } else {
-    k_umma_qprep<<<dim3((unsigned)xsq_nparts, kUQ), 256, 0, st>>>(xq, (int)Q, D, xpl, xsq_part, zero_word);
+  for (int g = 0; g < G; ++g) {
+    const float* xg = xq + (int64_t)g * kUQ * D;
+    __nv_bfloat16* pg = xpl + (int64_t)g * kUStack * D;
+    if (xsq) {
+      k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg);
+    } else {
+      k_umma_qprep<<<dim3((unsigned)L.xsq_nparts, kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg,
+                                                                     xsq_part + (int64_t)g * L.xsq_nparts * kUQ,
+                                                                     g == 0 ? zero_word : nullptr);
+    }
+    SDN_LAUNCHED();
   }
   g_prof.end(pid, st);
-  SDN_LAUNCHED();
 
   // phase A: split K (= D) so that roughly every SM gets one task
   const int row_tiles = (int)(L.npad / kUBankTile);
   const int kblocks = (int)(D / kUK);
-  const int64_t split_stride = L.npad * kUStack;
   pid = g_prof.begin("k_umma_dots", st);
-  k_umma_dots<<<dim3(row_tiles, L.ksplit), kUThreads, kUSmemBytes, st>>>(tm_x, tm_hiA, tm_loA, S_T, split_stride,
-                                                                        kblocks, L.ksplit, bf16_bank ? 0 : 1);
+  if (G == 1)
+    k_umma_dots<1><<<dim3(row_tiles, L.ksplit), UCfg<1>::kThreads, kUSmemBytes, st>>>(
+        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, L.group_stride_s, kblocks, L.ksplit, bf16_bank ? 0 : 1);
+  else
+    k_umma_dots<2><<<dim3(row_tiles, L.ksplit), UCfg<2>::kThreads, kUSmemBytes, st>>>(
+        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, L.group_stride_s, kblocks, L.ksplit, bf16_bank ? 0 : 1);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
 
-  // weights
-  SigLists lists_w{};
-  if (g_skip_negligible.load(std::memory_order_relaxed) && (L.npad / kUK) <= kMaxActive && (num || epi)) {
-    lists_w.flags = reinterpret_cast<int*>(w + L.off_f);
-    lists_w.count = reinterpret_cast<int*>(reinterpret_cast<float*>(lists_w.flags + L.npad / kUK) + kUQ);
-    lists_w.dense = lists_w.count + kUQ;
-  }
+  // weights, z, lists: per group
   pid = g_prof.begin("k_umma_weights", st);
-  k_umma_weights<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(S_T, split_stride, L.ksplit, sqnorm, xsq, xsq_part,
-                                                                      xsq_nparts, (int)N, (int)Q, inv2s2, power, alpha,
-                                                                      P, zpart, k_out, lists_w, (int)(L.npad / kUK));
-  SDN_LAUNCHED();
-  const int nflags = (int)(L.npad / kUK);
-  SigLists lists{};
-  lists.flags = reinterpret_cast<int*>(w + L.off_f);
-  float* kmax = reinterpret_cast<float*>(lists.flags + nflags);
-  lists.count = reinterpret_cast<int*>(kmax + kUQ);
-  lists.dense = lists.count + kUQ;
-  lists.rows = lists.dense + 4;
-  lists.ks = reinterpret_cast<float*>(lists.rows + kUQ * kListCap);
-  k_umma_zreduce<<<(unsigned)Q, 256, 0, st>>>(zpart, (int)(L.npad / kWRows), z, kmax, lists_w.flags ? lists.dense : nullptr);
-  SDN_LAUNCHED();
-  const bool sparse = g_skip_negligible.load(std::memory_order_relaxed) && nflags <= kMaxActive && (num || epi);
-  if (sparse) {
-    k_umma_siglist<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(P, kmax, (int)N, (int)Q, lists);
+  for (int g = 0; g < G; ++g) {
+    SigLists lw{};                 // what the weights kernel clears before anyone appends
+    if (sparse) { lw.flags = lists.flags; lw.count = lists.count + g * kUQ; lw.dense = lists.dense; }
+    k_umma_weights<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(
+        S_T + (int64_t)g * L.group_stride_s, L.split_stride, L.ksplit, sqnorm, xsq ? xsq + g * kUQ : nullptr,
+        xsq_part + (int64_t)g * L.xsq_nparts * kUQ, L.xsq_nparts, (int)N, group_rows(g), inv2s2, power, alpha,
+        P + (int64_t)g * L.npad * kUStack, zpart + (int64_t)g * L.zpart_stride,
+        k_out ? k_out + (int64_t)g * kUQ * N : nullptr, lw, nflags);
     SDN_LAUNCHED();
+  }
+  for (int g = 0; g < G; ++g) {
+    k_umma_zreduce<<<(unsigned)group_rows(g), 256, 0, st>>>(zpart + (int64_t)g * L.zpart_stride, (int)(L.npad / kWRows),
+                                                           z + g * kUQ, kmax + g * kUQ, sparse ? lists.dense : nullptr);
+    SDN_LAUNCHED();
+  }
+  if (sparse) {
+    for (int g = 0; g < G; ++g) {
+      SigLists lg = lists;
+      lg.count = lists.count + g * kUQ; lg.rows = lists.rows + g * kUQ * kListCap; lg.ks = lists.ks + g * kUQ * kListCap;
+      k_umma_siglist<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(P + (int64_t)g * L.npad * kUStack, kmax + g * kUQ,
+                                                                          (int)N, group_rows(g), lg);
+      SDN_LAUNCHED();
+    }
   }
   g_prof.end(pid, st);
   if (!num && !epi) return SDN_OK;   // z only (empirical_beta): no phase B
@@ -1076,21 +1168,15 @@ static int umma_partial_64(const void* planes, const float* sqnorm, int64_t N, i
     SDN_LAUNCHED();
   }
   pid = g_prof.begin("k_umma_accum", st);
-  const int gridx = nsplit == 1 ? std::min(dblocks, kNumSMs) : dblocks;
+  AccumLaunch al{};
+  al.tm_p = tm_p; al.tm_hi = tm_hiB; al.tm_lo = tm_loB; al.num = num; al.D = D; al.Q = (int)Q; al.rblocks = rblocks;
+  al.nsplit = nsplit; al.use_atomic = nsplit > 1 ? 1 : 0; al.use_lo = bf16_bank ? 0 : 1; al.p_group_rows = (int)L.npad;
+  al.flags = sparse ? lists.flags : nullptr; al.count = sparse ? lists.count : nullptr;
+  al.dense = sparse ? lists.dense : nullptr; al.e = e;
+  al.gridx = nsplit == 1 ? std::min(dblocks, kNumSMs) : dblocks;
   // chains longer than kBChunk row blocks are split over the two TMEM accumulators (fp32 register drain)
-  if ((rblocks + nsplit - 1) / nsplit > kBChunk) {
-    k_umma_accum<true><<<dim3(gridx, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
-                                                                     nsplit, nsplit > 1 ? 1 : 0, bf16_bank ? 0 : 1,
-                                                                     sparse ? lists.flags : nullptr,
-                                                                     sparse ? lists.count : nullptr,
-                                                                     sparse ? lists.dense : nullptr, e);
-  } else {
-    k_umma_accum<false><<<dim3(gridx, nsplit), kUThreads, kUSmemBytes, st>>>(tm_p, tm_hiB, tm_loB, num, D, (int)Q, rblocks,
-                                                                     nsplit, nsplit > 1 ? 1 : 0, bf16_bank ? 0 : 1,
-                                                                     sparse ? lists.flags : nullptr,
-                                                                     sparse ? lists.count : nullptr,
-                                                                     sparse ? lists.dense : nullptr, e);
-  }
+  al.chunked = (rblocks + nsplit - 1) / nsplit > kBChunk;
+  if (G == 1) launch_accum<1>(al, st); else launch_accum<2>(al, st);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   return SDN_OK;

@@ -89,6 +89,12 @@ SHAPES = [  # (name, Q, N, C, H, W)
     ("stream-d8192", 2, 50, 2, 64, 64),
     ("stream-d2048", 1, 40, 2, 32, 32),
     ("stream-sd3-512", 2, 40, 16, 64, 64),
+    # edges of the tcgen05 path: query groups of 64 (65, 130 rows), bank tiles of 128 (63, 129, 257 rows),
+    # a single 128-wide d-block
+    ("umma-q65", 65, 130, 4, 16, 16),
+    ("umma-q130", 130, 257, 2, 32, 32),
+    ("umma-n129-d128", 16, 129, 2, 8, 8),
+    ("umma-n63", 9, 63, 4, 16, 16),
 ]
 
 
