@@ -152,8 +152,11 @@ __device__ __forceinline__ USmem u_carve(unsigned char* raw) {
 }
 
 // ------------------------------------------------------------------------------------------ query planes
+// bf16 hi/lo planes of 64 query rows: hi part of row q at plane row q, lo part at plane row lo_rows + q.
+//   one group per pass : [64 hi | 64 lo] rows = ONE stacked 128-row MMA operand           (lo_rows = 64)
+//   two groups per pass: [128 hi] [128 lo]   = two 128-row operands, group g at rows 64 g (lo_rows = 128)
 __global__ void __launch_bounds__(256)
-k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes) {
+k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes, int lo_rows) {
   const int q = blockIdx.y;   // 0..63
   const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (j >= D) return;
@@ -171,13 +174,13 @@ k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
     for (int u = 0; u < 4; ++u) h[u] = l[u] = __float2bfloat16_rn(0.f);
   }
   *reinterpret_cast<uint2*>(planes + (int64_t)q * D + j) = *reinterpret_cast<const uint2*>(h);
-  *reinterpret_cast<uint2*>(planes + (int64_t)(kUQ + q) * D + j) = *reinterpret_cast<const uint2*>(l);
+  *reinterpret_cast<uint2*>(planes + (int64_t)(lo_rows + q) * D + j) = *reinterpret_cast<const uint2*>(l);
 }
 
 // Same, plus ||x_q||^2 partials (one per 1024-element chunk, summed by k_umma_weights) so that the batched
 // conditioning call needs no separate query-prepare launch.  grid (D/1024, 64).
 __global__ void __launch_bounds__(256)
-k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes,
+k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes, int lo_rows,
              float* __restrict__ xsq_part, float* __restrict__ zero_word) {
   __shared__ float red[33];
   if (zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *zero_word = 0.f;
@@ -200,15 +203,19 @@ k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
       for (int u = 0; u < 4; ++u) h[u] = l[u] = __float2bfloat16_rn(0.f);
     }
     *reinterpret_cast<uint2*>(planes + (int64_t)q * D + j) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(planes + (int64_t)(kUQ + q) * D + j) = *reinterpret_cast<const uint2*>(l);
+    *reinterpret_cast<uint2*>(planes + (int64_t)(lo_rows + q) * D + j) = *reinterpret_cast<const uint2*>(l);
   }
   ss = block_sum(ss, red);
   if (threadIdx.x == 0) xsq_part[(int64_t)blockIdx.x * kUQ + q] = ss;
 }
 
 // ------------------------------------------------------------------------------------------ phase A
-// grid (row tiles, k splits).  S_T [G][ksplit][Npad][128] fp32:
-//   S_T[g][s][i][r] = sum over K split s of X_g[r][d] * bank[i][d]      (r = stacked query row of group g).
+// grid (row tiles, k splits).  S_T [ksplit][Npad][128] fp32: S_T[s][i][r] = sum over K split s of X[r][d] * bank[i][d].
+//   G = 1: the 128 operand rows are 64 hi parts stacked on 64 lo parts; B = hi tile, then lo tile (2 MMAs per K step,
+//          the lo x lo product comes for free) and the dot of query q is S_T[..][q] + S_T[..][64 + q];
+//   G = 2: two 128-row operands, the hi parts and the lo parts of 128 queries; hi x hi, hi x lo and lo x hi go into
+//          ONE accumulator (3 MMAs per K step for twice the queries -- the tensor pipe, not HBM, would bound four)
+//          and S_T[..][r] is the complete dot of query r.
 //
 // The tensor core adds into its fp32 accumulator with truncation, and near a negative the distance is the
 // small difference of large dot products, so long accumulation chains cost accuracy (measured: 43 K-blocks in
@@ -216,11 +223,14 @@ k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
 // kUChunk K-blocks and the epilogue warps drain the finished one into fp32 registers (round-to-nearest adds).
 constexpr int kUChunk = 4;
 
+constexpr int kUThreadsA = 192;   // TMA warp, MMA warp, 4 epilogue warps
+constexpr uint32_t kAccColsA = 128;
+
 template <int G>
-__global__ void __launch_bounds__(UCfg<G>::kThreads, 1)
+__global__ void __launch_bounds__(kUThreadsA, 1)
 k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
             const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int64_t split_stride,
-            int64_t group_stride, int kblocks_total, int ksplit, int use_lo) {
+            int kblocks_total, int ksplit, int use_lo) {
   using C = UCfg<G>;
   extern __shared__ unsigned char smem_raw[];
   const USmem sm = u_carve(smem_raw);
@@ -244,14 +254,14 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int npre = min(nkb, C::kStages);
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4 * G); }
+    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the first stages need nothing but this thread's own barriers: their HBM latency overlaps the TMEM
     // allocation and the start-up barrier (the kernel is fill/drain bound at N ~ 3000)
     u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
     for (int i = 0; i < npre; ++i) load_stage(i);
   }
-  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * C::kAccCols);
+  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kAccColsA);
   u_fence_before();
   __syncthreads();
   u_fence_after();
@@ -273,7 +283,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((c >> 1) + 1) & 1));
           u_fence_after();
         }
-        const uint32_t acc = tmem + (uint32_t)buf * C::kAccCols;
+        const uint32_t acc = tmem + (uint32_t)buf * kAccColsA;
         const int i1 = min(nkb, (c + 1) * kUChunk);
         for (int i = c * kUChunk; i < i1; ++i) {
           const int s = i % C::kStages;
@@ -284,11 +294,12 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           for (int kk = 0; kk < kUK / 16; ++kk) {
             const uint64_t bh = u_desc(base + C::kHiOff + kk * 32, 16, 1024);
             const uint64_t bl = u_desc(base + C::kLoOff + kk * 32, 16, 1024);
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const uint64_t a = u_desc(base + (uint32_t)g * kTileBytes + kk * 32, 16, 1024);
-              u_mma(acc + (uint32_t)g * kUBankTile, a, bh, idesc, (i > c * kUChunk || kk > 0) ? 1u : 0u);
-              if (use_lo) u_mma(acc + (uint32_t)g * kUBankTile, a, bl, idesc, 1u);
+            const uint64_t a0 = u_desc(base + kk * 32, 16, 1024);                 // G = 1: stacked hi|lo; G = 2: hi parts
+            u_mma(acc, a0, bh, idesc, (i > c * kUChunk || kk > 0) ? 1u : 0u);
+            if (use_lo) u_mma(acc, a0, bl, idesc, 1u);
+            if constexpr (G == 2) {
+              const uint64_t a1 = u_desc(base + kTileBytes + kk * 32, 16, 1024);  // lo parts of the 128 queries
+              u_mma(acc, a1, bh, idesc, 1u);
             }
           }
           u_commit(&sm.empty[s]);
@@ -297,10 +308,8 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       }
     }
   } else {
-    // epilogue: warps 2..5 drain group 0, warps 6..9 group 1; a warp may touch TMEM lanes [32*(w%4), +32);
-    // lane index = stacked query row
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); lane index = operand row (stacked / plain query row)
     const int lq = warp & 3;
-    const int g = (warp - 2) >> 2;
     float sum[kUBankTile];
 #pragma unroll
     for (int j = 0; j < kUBankTile; ++j) sum[j] = 0.f;
@@ -308,7 +317,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const int buf = c & 1;
       u_mbar_wait(&sm.acc_full[buf], (uint32_t)((c >> 1) & 1));
       u_fence_after();
-      const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)buf * C::kAccCols + (uint32_t)(g * kUBankTile);
+      const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)buf * kAccColsA;
 #pragma unroll
       for (int cc = 0; cc < kUBankTile / 32; ++cc) {
         float v[32];
@@ -322,7 +331,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     // every K split owns its own partial buffer: plain coalesced stores, summed by k_umma_weights
     const int r = lq * 32 + lane;
-    float* dst = S_T + (int64_t)g * group_stride + (int64_t)blockIdx.y * split_stride + (int64_t)row0 * kUStack + r;
+    float* dst = S_T + (int64_t)blockIdx.y * split_stride + (int64_t)row0 * kUStack + r;
 #pragma unroll
     for (int j = 0; j < kUBankTile; ++j) dst[(int64_t)j * kUStack] = sum[j];
   }
@@ -330,7 +339,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   __syncthreads();
   if (warp == 1) {
     u_fence_after();
-    u_tmem_dealloc(tmem, 2 * C::kAccCols);
+    u_tmem_dealloc(tmem, 2 * kAccColsA);
   }
 }
 
@@ -358,8 +367,10 @@ __device__ __forceinline__ void siglist_clear(const SigLists& L, int nflags) {
 // which phase B reads as an MN-major B operand.  Everything is coalesced; block = 4 bank rows x 64 query rows.
 constexpr int kWRows = 4;
 
+// The dot of query row q is S_T[..][col0 + q] (+ S_T[..][col0 + lo_off + q] when lo_off > 0: stacked operand).
 __global__ void __launch_bounds__(kWRows * kUQ)
-k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, const float* __restrict__ sqnorm,
+k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, int col0, int lo_off,
+               const float* __restrict__ sqnorm,
                const float* __restrict__ xsq, const float* __restrict__ xsq_part, int xsq_nparts, int N, int Q,
                float inv2s2, int power, float alpha, __nv_bfloat16* __restrict__ P, float* __restrict__ zpart,
                float* __restrict__ k_out, SigLists lists, int nflags) {
@@ -372,8 +383,8 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
   float dot = 0.f;
 #pragma unroll 4
   for (int sp = 0; sp < ksplit; ++sp) {
-    const float* p = s + (int64_t)sp * split_stride;
-    dot += p[q] + p[kUQ + q];
+    const float* p = s + (int64_t)sp * split_stride + col0;
+    dot += lo_off > 0 ? p[q] + p[lo_off + q] : p[q];
   }
   float k = 0.f;
   if (i < N && q < Q) {
@@ -913,7 +924,7 @@ struct UmmaLayout {
   int xsq_nparts;
   size_t off_x, off_s, off_p, off_z, off_f, off_q, total;
   // per-group strides (elements)
-  int64_t split_stride, group_stride_s, zpart_stride;
+  int64_t split_stride, zpart_stride;
 };
 UmmaLayout umma_layout(int64_t Q, int64_t N, int64_t D) {
   UmmaLayout L;
@@ -923,13 +934,12 @@ UmmaLayout umma_layout(int64_t Q, int64_t N, int64_t D) {
   L.nflags = (int)(L.npad / kUK);
   L.xsq_nparts = (int)cdiv(D, 1024);
   L.split_stride = L.npad * kUStack;
-  L.group_stride_s = (int64_t)L.ksplit * L.split_stride;
   L.zpart_stride = (L.npad / kWRows) * kUStack + 64;
   const size_t G = (size_t)L.G;
   size_t o = 0;
-  L.off_x = o; o += G * kUStack * D * 2;                     // X planes [G][128][D]
+  L.off_x = o; o += G * kUStack * D * 2;                     // X planes [128 G][D] (layout: k_umma_xprep)
   o = (o + 255) / 256 * 256;
-  L.off_s = o; o += G * L.group_stride_s * 4;                // S^T [G][ksplit][Npad][128], one partial per K split
+  L.off_s = o; o += (size_t)L.ksplit * L.split_stride * 4;   // S^T [ksplit][Npad][128], one partial per K split
   o = (o + 255) / 256 * 256;
   L.off_p = o; o += G * kUStack * L.npad * 2;                // P planes [G][Npad][128]
   o = (o + 255) / 256 * 256;
@@ -1095,11 +1105,11 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   int pid = g_prof.begin(xsq ? "k_umma_xprep" : "k_umma_qprep", st);
   for (int g = 0; g < G; ++g) {
     const float* xg = xq + (int64_t)g * kUQ * D;
-    __nv_bfloat16* pg = xpl + (int64_t)g * kUStack * D;
+    __nv_bfloat16* pg = xpl + (int64_t)g * kUQ * D;      // hi part of the group's row 0; lo parts G * 64 rows below
     if (xsq) {
-      k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg);
+      k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg, G * kUQ);
     } else {
-      k_umma_qprep<<<dim3((unsigned)L.xsq_nparts, kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg,
+      k_umma_qprep<<<dim3((unsigned)L.xsq_nparts, kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg, G * kUQ,
                                                                      xsq_part + (int64_t)g * L.xsq_nparts * kUQ,
                                                                      g == 0 ? zero_word : nullptr);
     }
@@ -1112,11 +1122,11 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   const int kblocks = (int)(D / kUK);
   pid = g_prof.begin("k_umma_dots", st);
   if (G == 1)
-    k_umma_dots<1><<<dim3(row_tiles, L.ksplit), UCfg<1>::kThreads, kUSmemBytes, st>>>(
-        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, L.group_stride_s, kblocks, L.ksplit, bf16_bank ? 0 : 1);
+    k_umma_dots<1><<<dim3(row_tiles, L.ksplit), kUThreadsA, kUSmemBytes, st>>>(
+        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1);
   else
-    k_umma_dots<2><<<dim3(row_tiles, L.ksplit), UCfg<2>::kThreads, kUSmemBytes, st>>>(
-        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, L.group_stride_s, kblocks, L.ksplit, bf16_bank ? 0 : 1);
+    k_umma_dots<2><<<dim3(row_tiles, L.ksplit), kUThreadsA, kUSmemBytes, st>>>(
+        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
 
@@ -1126,7 +1136,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     SigLists lw{};                 // what the weights kernel clears before anyone appends
     if (sparse) { lw.flags = lists.flags; lw.count = lists.count + g * kUQ; lw.dense = lists.dense; }
     k_umma_weights<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(
-        S_T + (int64_t)g * L.group_stride_s, L.split_stride, L.ksplit, sqnorm, xsq ? xsq + g * kUQ : nullptr,
+        S_T, L.split_stride, L.ksplit, g * kUQ, G == 1 ? kUQ : 0, sqnorm, xsq ? xsq + g * kUQ : nullptr,
         xsq_part + (int64_t)g * L.xsq_nparts * kUQ, L.xsq_nparts, (int)N, group_rows(g), inv2s2, power, alpha,
         P + (int64_t)g * L.npad * kUStack, zpart + (int64_t)g * L.zpart_stride,
         k_out ? k_out + (int64_t)g * kUQ * N : nullptr, lw, nflags);
