@@ -141,8 +141,32 @@ def cpu_reference_arm(wl, steps, warmup, sample_q=4):
 
 
 # ----------------------------------------------------------------------------------- main
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries print banners on stdout (NCCL: 'NCCL version ...'); the contract is ONE JSON line there.  Point fd 1
+    at stderr for the whole run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -175,7 +199,7 @@ def main():
                      "gpu_launches": 0})
         line["config"] = dict(base["config"], note="reference arm: the reference is pure Python with no "
                               "package to install; its CPU op chain is timed via the oracle port on the host cores")
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -424,7 +448,7 @@ def main():
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

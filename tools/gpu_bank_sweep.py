@@ -92,15 +92,17 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        t = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(e0, e1))], dtype=torch.float64, device=dev)
+        per = sorted(a.elapsed_time(b) for a, b in zip(e0, e1))
+        t = torch.tensor([sum(per), per[len(per) // 2], per[-1]], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item()) / args.steps
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)          # every statistic: max over ranks
+        ms, ms_median, ms_max = float(t[0].item()) / args.steps, float(t[1].item()), float(t[2].item())
         checksum = float(x.double().sum().item())
         absmax = float((x - x_src).abs().max().item())
         if rank == 0:
             one_pass = n * D * 4.0
-            print(json.dumps({"N": n, "Q": Q, "n_gpus": world, "ms_per_step": ms, "projections_per_s": Q / (ms * 1e-3),
+            print(json.dumps({"N": n, "Q": Q, "n_gpus": world, "ms_per_step": ms, "ms_median": ms_median, "ms_slowest_step": ms_max,
+                              "projections_per_s": Q / (ms * 1e-3),
                               "one_pass_GBs": one_pass / (ms * 1e-3) / 1e9,
                               "frac_of_world_x_peak": one_pass / (ms * 1e-3) / 1e9 / (world * peak),
                               "peak_GBs_per_gpu": peak, "checksum": checksum, "max_correction": absmax,
