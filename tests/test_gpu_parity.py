@@ -372,12 +372,13 @@ def test_bf16_bank_mode_reports_its_own_error(nv):
         assert rel(got["weights"], want["weights"]) <= tol_w, regime
 
 
+@pytest.mark.parametrize("nq", [48, 100])
 @pytest.mark.parametrize("regime,sigma", [("near", 1.0), ("mid", 1.0), ("x0", 3.15), ("far", 13.15)])
-def test_block_sparse_accumulate_equals_dense(nv, regime, sigma):
+def test_block_sparse_accumulate_equals_dense(nv, regime, sigma, nq):
     """SDN_OPT_SKIP_NEGLIGIBLE: skipping row blocks whose weights are < 1e-9 of the query's largest weight must
     not change the result beyond fp32 summation noise, in peaked (sigma = 1) and flat (sigma = 13) regimes."""
     bank = orc.synthetic_bank(1000, 4, 64, 64)
-    x = orc.synthetic_queries(bank, 48, regime)
+    x = orc.synthetic_queries(bank, nq, regime)
     want = orc.conditioning_fast(x.numpy(), bank.numpy(), scale=0.33, sigma=sigma)
     out = {}
     for on in (1, 0):
@@ -390,16 +391,18 @@ def test_block_sparse_accumulate_equals_dense(nv, regime, sigma):
     assert rel(out[1]["denom"], out[0]["denom"]) == 0.0
 
 
-def test_block_sparse_list_overflow_falls_back_to_tensor_core_pass(nv):
+@pytest.mark.parametrize("nq", [24, 72])
+def test_block_sparse_list_overflow_falls_back_to_tensor_core_pass(nv, nq):
     """Peaked weights (z / kmax ~ 1) but MORE than 32 rows above the 1e-9 significance bound: the per-query lists
-    overflow, the listed kernel must step aside and the block-sparse tcgen05 pass must produce the result."""
+    overflow, the listed kernel must step aside and the block-sparse tcgen05 pass must produce the result.
+    72 query rows = two query groups in one pass: the row-block flags are the union over the groups."""
     g = torch.Generator().manual_seed(3)
     centres = torch.randn(4, 4, 64, 64, generator=g)
     bank = torch.cat([centres] + [c[None] + 0.3 * torch.randn(70, 4, 64, 64, generator=g) for c in centres]
                      + [5.0 + torch.randn(356, 4, 64, 64, generator=g)])   # 4 centres + 280 clustered + 356 far rows
     perm = torch.randperm(bank.shape[0], generator=g)
     bank = bank[perm].contiguous()
-    x = torch.stack([centres[i % 4] + 0.02 * torch.randn(4, 64, 64, generator=g) for i in range(24)])
+    x = torch.stack([centres[i % 4] + 0.02 * torch.randn(4, 64, 64, generator=g) for i in range(nq)])
     want = orc.closed_form(x.numpy(), bank.numpy(), sigma=1.0)
     nsig = (want["k"] >= 1e-9 * want["k"].max(1, keepdims=True)).sum(1)
     assert nsig.min() > 32 and (want["Z"] / want["k"].max(1)).max() < 32      # the case this test is about
