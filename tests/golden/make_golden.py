@@ -55,6 +55,24 @@ def fast_cases(mod, tag, c, h, w, n, out):
             out[key + "/item"] = np.float64(d["mean_x_0_hat"])
 
 
+def batched_cases(out):
+    """Batched queries (the CFG-doubled batch): 16 and 70 rows -- the second needs two query groups of 64 in the
+    tcgen05 path.  D = 2*8*8 = 128 (one d-block of that path) keeps the file small; the negative mean is not stored,
+    it is (x - x0) / scale."""
+    c, h, w, n = 2, 8, 8, 130
+    bank = synthetic_bank(n, c, h, w, seed=2468)
+    out["batched/bank"] = bank.numpy()
+    proc = build(ref_fast, "kernel_fast", bank, scale=0.03, sigma=3.55)
+    for q in (16, 70):
+        for regime in ("near", "mid"):
+            x = synthetic_queries(bank, q, regime, seed=1357 + q)
+            d = proc.conditioning(x.clone(), beta_threshold=False)
+            key = f"batched/q{q}/{regime}"
+            out[key + "/x"] = x.numpy()
+            out[key + "/x0"] = d["x_0_hat"].numpy()
+            out[key + "/item"] = np.float64(d["mean_x_0_hat"])
+
+
 def threshold_cases(out):
     c, h, w, n = 4, 8, 8, 37
     bank = synthetic_bank(n, c, h, w, seed=1234)
@@ -179,6 +197,15 @@ def known_answers():
 
 
 def main():
+    if "--batched-only" in sys.argv:        # added later: leaves the other fixture files untouched
+        fx = {}
+        batched_cases(fx)
+        np.savez_compressed(os.path.join(HERE, "batched_cases.npz"), **fx)
+        print("batched_cases.npz written to", HERE)
+        return
+    fx = {}
+    batched_cases(fx)
+    np.savez_compressed(os.path.join(HERE, "batched_cases.npz"), **fx)
     fx = {}
     fast_cases(ref_fast, "fast", 4, 8, 8, 37, fx)
     fast_cases(ref_sdv3, "sdv3", 16, 4, 4, 29, fx)

@@ -177,6 +177,24 @@ def test_dropin_fast_against_reference_goldens(tag, kind, tmp_path):
             assert abs(float(d["mean_x_0_hat"]) - float(fx[key + "/item"])) <= TOL * abs(float(fx[key + "/item"])) + 1e-12
 
 
+@pytest.mark.parametrize("q", [16, 70])
+def test_dropin_batched_against_reference_goldens(q, tmp_path):
+    """CFG-doubled batches through the drop-in fast module vs outputs of the unmodified reference: 16 rows take the
+    tcgen05 path, 70 rows its two-query-group pass."""
+    fx = np.load(os.path.join(G, "batched_cases.npz"))
+    proc = _build("fast", "kernel_fast", fx["batched/bank"], tmp_path, scale=0.03, sigma=3.55)
+    for regime in ("near", "mid"):
+        key = f"batched/q{q}/{regime}"
+        xin = torch.from_numpy(fx[key + "/x"]).cuda()
+        d = proc.conditioning(xin, beta_threshold=False)
+        assert d["x_0_hat"] is xin
+        assert rel(xin, fx[key + "/x0"]) <= TOL
+        # the correction itself (x - x0 = scale * neg), not hidden behind the magnitude of x
+        corr_ref = fx[key + "/x"] - fx[key + "/x0"]
+        assert rel(torch.from_numpy(fx[key + "/x"]) - xin.cpu(), corr_ref) <= TOL
+        assert abs(float(d["mean_x_0_hat"]) - float(fx[key + "/item"])) <= TOL * abs(float(fx[key + "/item"])) + 1e-12
+
+
 def test_dropin_threshold_against_reference_goldens(tmp_path):
     fx = np.load(os.path.join(G, "threshold_cases.npz"))
     for sigma in (3.15, 1.0, 13.15):

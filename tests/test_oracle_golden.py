@@ -37,6 +37,19 @@ def test_fast_closed_form_matches_reference(fast_fx, tag, sdv3, q, regime):
     assert abs(r["mean_x_0_hat"] - float(fast_fx[key + "/item"])) < 1e-6 * max(1.0, abs(r["mean_x_0_hat"]))
 
 
+@pytest.mark.parametrize("q", [16, 70])
+@pytest.mark.parametrize("regime", ["near", "mid"])
+def test_batched_queries_match_reference(q, regime):
+    """CFG-doubled batches (16 and 70 query rows) through the reference's fast module."""
+    fx = np.load(os.path.join(G, "batched_cases.npz"))
+    key = f"batched/q{q}/{regime}"
+    x = fx[key + "/x"]
+    r = orc.conditioning_fast(x, fx["batched/bank"], scale=0.03, sigma=1.0)
+    assert rel(r["x_0_hat"], fx[key + "/x0"]) < 1e-6
+    assert rel(r["neg"], (x - fx[key + "/x0"]) / 0.03) < 5e-4      # (x - x0) / scale loses digits to cancellation
+    assert abs(r["mean_x_0_hat"] - float(fx[key + "/item"])) < 1e-6 * max(1.0, abs(r["mean_x_0_hat"]))
+
+
 @pytest.mark.parametrize("q", [1, 3])
 @pytest.mark.parametrize("regime", ["far", "x0", "near", "mid"])
 def test_materialised_port_matches_reference(fast_fx, q, regime):
