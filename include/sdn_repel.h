@@ -15,8 +15,12 @@
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - no hidden allocation: scratch is caller-provided, its size comes from
- *     the matching *_workspace_bytes() call (the *_host convenience calls are
- *     the exception: they own a cached pinned/device staging area);
+ *     the matching *_workspace_bytes() call.  Two exceptions: the *_host convenience
+ *     calls own a cached device staging area, and SDN_PATH_FLASH owns ~9 MB of
+ *     per-device synchronisation memory (exchange rings of its persistent grid,
+ *     allocated and zeroed at its first call on a device -- so make that first call
+ *     outside a CUDA-graph capture; calls of that path on one device must be stream-ordered
+ *     with each other, its grid fills the GPU anyway);
  *   - return value: 0 ok; <0 invalid argument (SDN_E_*); >0 a cudaError_t.
  *   - all tensors are contiguous row-major fp32 unless stated.
  *
@@ -51,8 +55,12 @@ enum {
   SDN_PATH_GENERIC = 1,   /* CUDA-core two-phase kernels, any shape */
   SDN_PATH_STREAM = 2,    /* one-pass cluster kernel, GEMV-shaped (small Q) */
   SDN_PATH_UMMA = 3,      /* tcgen05 / TMEM / TMA two-phase kernels, batched Q */
-  SDN_PATH_UMMA_BF16 = 4  /* same kernels reading ONLY the bf16 hi plane of the bank: half the bytes per pass,
+  SDN_PATH_UMMA_BF16 = 4, /* same kernels reading ONLY the bf16 hi plane of the bank: half the bytes per pass,
                              outside the 1e-3 parity tolerance near a negative; explicit opt-in, never AUTO */
+  SDN_PATH_FLASH = 5      /* ONE-pass tcgen05 kernel, batched Q: every bank tile stays in shared memory between the
+                             distance contraction and the weighted accumulation (persistent grid of D/128 CTAs,
+                             cross-CTA reduction over DSMEM + L2).  D % 1024 == 0, 8192 <= D <= 16384 (SD-1.4 latents);
+                             AUTO prefers it over SDN_PATH_UMMA whenever the shape fits */
 };
 
 /* Epilogue flags (bit-or). */
@@ -81,6 +89,10 @@ int sdn_set_option(int32_t key, int32_t value);
  * that kernel's end event), 0 when i is out of range.  bench.py uses it for the roofline of the dominant kernel. */
 void sdn_profile_enable(int32_t on);
 int32_t sdn_profile_read(int32_t index, char* name_out, int32_t name_cap, float* ms_out);
+
+/* After a kernel of the one-pass path trapped on a bounded wait (CUDA error "unspecified launch failure"), the
+ * first words of its host-mapped diagnostic record: {code, CTA, thread, tile, extra}.  Returns 0 when there is none. */
+int32_t sdn_debug_read(uint32_t* words_out, int32_t n);
 
 /* ---- bank -------------------------------------------------------------------------------
  * Derived data of the proj_ref tensor, computed once at load (fast.py:109-111 loads the tensor;
@@ -188,18 +200,22 @@ int sdn_epilogue_flow(const float* num, const float* z, int64_t Q, int64_t D,
  * no channel normalisation (fast.py:120-132, threshold.py:171-193).
  *   Q <= 8 : the one-pass kernel computes ||x||^2 itself and the per-cluster reduction applies the correction
  *            (2 launches);
- *   Q > 8  : (needs `planes` and z_out) query planes + ||x||^2 in one kernel, correction fused into the epilogue
+ *   Q > 8  : SDN_PATH_FLASH shapes: ONE launch (query planes, ||x||^2, both contractions, the cross-CTA reduction
+ *            and the correction in the same persistent kernel; the bank is read once); otherwise
+ *            (needs `planes` and z_out) query planes + ||x||^2 in one kernel, correction fused into the epilogue
  *            of phase B (5 launches instead of 8).  One pass over the bank serves up to 128 query rows (two groups
  *            of 64 sharing every bank tile; the small element-wise kernels run once per group), more rows take
  *            ceil(Q / 128) passes.
  * x0_inout [Q,D] is corrected in place; num_out / neg_out / k_out are optional extra outputs; mean_out is zeroed
- * by the call.  Returns SDN_E_UNSUPPORTED for shapes neither fused path takes (callers then use the three-call
+ * by the call.  `path`: SDN_PATH_AUTO, or SDN_PATH_STREAM / SDN_PATH_UMMA / SDN_PATH_FLASH to force one family.
+ * Returns SDN_E_UNSUPPORTED for shapes the selected fused path does not take (callers then use the three-call
  * sequence).  Workspace: sdn_repel_workspace_bytes(Q, N, D, SDN_PATH_AUTO). */
 int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* planes, int64_t N, int64_t D,
                            float* x0_inout, int64_t Q, float inv_two_sigma_sq, int32_t dist_power, float bank_alpha,
                            float eps, float scale, float gate_threshold, int32_t flags,
                            float* num_out, float* z_out, float* neg_out, float* denom_out, int32_t* gate_out,
-                           float* mean_out, float* k_out, void* workspace, size_t workspace_bytes, void* stream);
+                           float* mean_out, float* k_out, void* workspace, size_t workspace_bytes, int32_t path,
+                           void* stream);
 
 /* ---- N-sharded banks: merge + correction in one kernel over NVLink peer memory ------------------------------
  * Replaces "all-reduce(num|z) then sdn_epilogue_correct" when the bank is sharded by rows over `world` GPUs of one

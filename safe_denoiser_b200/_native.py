@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdn_repel.so")
 
-PATH_AUTO, PATH_GENERIC, PATH_STREAM, PATH_UMMA, PATH_UMMA_BF16 = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_GENERIC, PATH_STREAM, PATH_UMMA, PATH_UMMA_BF16, PATH_FLASH = 0, 1, 2, 3, 4, 5
 EPI_GATE, EPI_RETURN_NEG = 1, 2
 
 _lib = None
@@ -22,6 +22,7 @@ SIGNATURES = {
     "sdn_error_string": (C.c_char_p, [C.c_int]),
     "sdn_launch_count": (C.c_uint64, []),
     "sdn_set_option": (C.c_int, [_i32, _i32]),
+    "sdn_debug_read": (_i32, [C.POINTER(C.c_uint32), _i32]),
     "sdn_profile_enable": (None, [_i32]),
     "sdn_profile_read": (_i32, [_i32, C.c_char_p, _i32, C.POINTER(C.c_float)]),
     "sdn_bank_prepare": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
@@ -38,7 +39,7 @@ SIGNATURES = {
                                     _f, _f, _f, _f, _p, _p, _p, _p, _p, _p]),
     "sdn_epilogue_flow": (C.c_int, [_p, _p, _i64, _i64, _f, _f, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p]),
     "sdn_conditioning_fused": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _f, _i32, _f, _f, _f, _f, _i32,
-                                         _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+                                         _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i32, _p]),
     "sdn_shard_merge_correct": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i64, _i64, _f, _f, _f, _i32,
                                           _p, _p, _p, _p, _p]),
     "sdn_sparse_repel": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _f, _f, _p, _p, _p, _sz, _p]),
@@ -76,6 +77,14 @@ def check(rc):
     if rc != 0:
         msg = lib().sdn_error_string(rc).decode()
         raise RuntimeError(f"sdn_repel call failed ({rc}): {msg}")
+
+
+def debug_read():
+    """Diagnostic record of a one-pass kernel that trapped on a bounded wait: [code, cta, thread, tile, extra] or None."""
+    buf = (C.c_uint32 * 8)()
+    if not lib().sdn_debug_read(buf, 8):
+        return None
+    return [int(v) for v in buf]
 
 
 def ptr(t):

@@ -19,6 +19,7 @@ static bool batched(int64_t Q, int64_t N) { return Q > 8 || (Q > 4 && N >= 1024)
 
 static int pick_path(int32_t path, int64_t Q, int64_t N, int64_t D, const void* planes) {
   if (path == SDN_PATH_AUTO) {
+    if (flash_supported(Q, N, D, planes) && batched(Q, N)) return SDN_PATH_FLASH;
     if (umma_supported(Q, N, D, planes) && batched(Q, N)) return SDN_PATH_UMMA;
     if (stream_supported(Q, N, D)) return SDN_PATH_STREAM;
     return SDN_PATH_GENERIC;
@@ -74,6 +75,11 @@ int32_t sdn_profile_read(int32_t index, char* name_out, int32_t name_cap, float*
   return 1;
 }
 
+int32_t sdn_debug_read(uint32_t* words_out, int32_t n) {
+  if (!words_out || n <= 0) return 0;
+  return flash_diag_read(words_out, n);
+}
+
 int32_t sdn_repel_path(int64_t Q, int64_t N, int64_t D, int32_t has_planes, int32_t path) {
   if (Q <= 0 || N <= 0 || D <= 0) return SDN_E_SHAPE;
   static const char dummy = 0;
@@ -103,7 +109,17 @@ int sdn_repel_partial(const float* bank, const float* sqnorm, const void* planes
   g_prof.reset();
   int chosen = pick_path(path, Q, N, D, planes);
   if (!num_out && chosen == SDN_PATH_STREAM) chosen = SDN_PATH_GENERIC;   // z only: phase A kernels only
+  if (!num_out && chosen == SDN_PATH_FLASH) chosen = SDN_PATH_UMMA;
   switch (chosen) {
+    case SDN_PATH_FLASH: {
+      if (!flash_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
+      const int rc = flash_run(planes, sqnorm, N, D, xq, Q, inv_two_sigma_sq, dist_power, bank_alpha, num_out, z_out,
+                               k_out, nullptr, st);
+      // the grid cannot be co-resident on this device (MIG slice, another context): the two-phase kernels can
+      if (rc != SDN_E_UNSUPPORTED || path == SDN_PATH_FLASH || !umma_supported(Q, N, D, planes)) return rc;
+      return umma_partial(planes, sqnorm, N, D, xq, xsq, Q, inv_two_sigma_sq, dist_power, bank_alpha,
+                          num_out, z_out, k_out, workspace, workspace_bytes, st, false);
+    }
     case SDN_PATH_STREAM:
       if (!bank) return SDN_E_NULL;
       if (!stream_supported(Q, N, D)) return SDN_E_UNSUPPORTED;
@@ -142,8 +158,9 @@ int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* p
                            float* x0_inout, int64_t Q, float inv_two_sigma_sq, int32_t dist_power, float bank_alpha,
                            float eps, float scale, float gate_threshold, int32_t flags, float* num_out, float* z_out,
                            float* neg_out, float* denom_out, int32_t* gate_out, float* mean_out, float* k_out,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+                           void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
   if (!sqnorm || !x0_inout || (!bank && !planes)) return SDN_E_NULL;
+  if (path != SDN_PATH_AUTO && path != SDN_PATH_STREAM && path != SDN_PATH_UMMA && path != SDN_PATH_FLASH) return SDN_E_PARAM;
   if (Q <= 0 || N <= 0 || D <= 0) return SDN_E_SHAPE;
   if (dist_power != 1 && dist_power != 2) return SDN_E_PARAM;
   if (D % 4 != 0 || (bank && !aligned16(bank)) || !aligned16(x0_inout) || (num_out && !aligned16(num_out)) ||
@@ -151,7 +168,18 @@ int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* p
     return SDN_E_ALIGN;
   g_prof.reset();
   cudaStream_t st = (cudaStream_t)stream;
-  if (batched(Q, N) && planes && z_out && umma_supported(Q, N, D, planes)) {
+  const bool want_batched = path == SDN_PATH_AUTO ? batched(Q, N) : path != SDN_PATH_STREAM;
+  if (path == SDN_PATH_FLASH && !flash_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
+  if (want_batched && (path == SDN_PATH_AUTO || path == SDN_PATH_FLASH) && flash_supported(Q, N, D, planes)) {
+    FlashEpi e{};
+    e.fused = 1; e.eps = eps; e.scale = scale; e.gate_thr = gate_threshold; e.flags = flags;
+    e.x0 = x0_inout; e.neg_out = neg_out; e.denom_out = denom_out; e.gate_out = gate_out; e.mean_out = mean_out;
+    e.inv_qd = 1.f / (float)(Q * D);
+    const int rc = flash_run(planes, sqnorm, N, D, x0_inout, Q, inv_two_sigma_sq, dist_power, bank_alpha, num_out, z_out,
+                             k_out, &e, st);
+    if (rc != SDN_E_UNSUPPORTED || path == SDN_PATH_FLASH) return rc;
+  }
+  if (want_batched && planes && z_out && umma_supported(Q, N, D, planes)) {
     if (!workspace || workspace_bytes < umma_workspace_bytes(Q, N, D)) return SDN_E_WORKSPACE;
     return umma_conditioning(planes, sqnorm, N, D, x0_inout, Q, inv_two_sigma_sq, dist_power, bank_alpha, eps, scale,
                              gate_threshold, flags, num_out, z_out, neg_out, denom_out, gate_out, mean_out, k_out,
@@ -240,7 +268,7 @@ int sdn_conditioning_host(const float* bank, const float* sqnorm, const void* pl
   int rc = SDN_E_UNSUPPORTED;
   if (normalize_C == 0 && path == SDN_PATH_AUTO)      // plain query: the few-launch sequence when the shape allows
     rc = sdn_conditioning_fused(bank, sqnorm, planes, N, D, x0, Q, inv_two_sigma_sq, dist_power, bank_alpha, eps, scale,
-                                0.f, 0, nullptr, z, nullptr, denom, nullptr, nullptr, nullptr, wsp, ws, stream);
+                                0.f, 0, nullptr, z, nullptr, denom, nullptr, nullptr, nullptr, wsp, ws, SDN_PATH_AUTO, stream);
   if (rc == SDN_E_UNSUPPORTED) {
     rc = sdn_query_prepare(x0, nullptr, 1.f, 0.f, Q, D, normalize_C, nullptr, normalize_C > 0 ? xq : nullptr, xsq,
                            stream);

@@ -1,5 +1,7 @@
 // Internal launch functions shared between translation units (not part of the C ABI).
 #pragma once
+#include <cuda.h>
+
 #include "sdn_common.cuh"
 
 namespace sdn {
@@ -48,5 +50,23 @@ int umma_conditioning(const void* planes, const float* sqnorm, int64_t N, int64_
                       float inv_two_sigma_sq, int power, float alpha, float eps, float scale, float gate_thr,
                       int flags, float* num_out, float* z, float* neg_out, float* denom_out, int32_t* gate_out,
                       float* mean_out, float* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// 2-D bf16 row-major tensor [rows][cols] -> TMA descriptor with box [box_rows][box_cols], 128-byte swizzle.
+int tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
+
+// ---- one-pass tcgen05 path for batched calls (sdn_flash.cu): the bank is read once ----
+struct FlashEpi {
+  // fused != 0: the correction of conditioning() runs in the kernel's epilogue (otherwise num_out / z_out only)
+  int fused;
+  float eps, scale, gate_thr; int flags;
+  float* x0; float* neg_out; float* denom_out; int32_t* gate_out; float* mean_out; float inv_qd;
+  int zero_mean;        // CTA 0 zeroes mean_out at start
+};
+bool flash_shape_ok(int64_t Q, int64_t N, int64_t D);
+bool flash_supported(int64_t Q, int64_t N, int64_t D, const void* planes);
+int flash_run(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq, int64_t Q,
+              float inv_two_sigma_sq, int power, float alpha, float* num_out, float* z_out, float* k_out,
+              const FlashEpi* epi, cudaStream_t st);
+int flash_diag_read(uint32_t* out, int n);
 
 }  // namespace sdn

@@ -196,7 +196,8 @@ class Projector:
         L = nv.lib()
         st = nv.current_stream()
         Q, xf = self._flat_query(x0)
-        if ((self._batched(Q) and self.path == nv.PATH_AUTO) or self.path in (nv.PATH_UMMA, nv.PATH_UMMA_BF16)) \
+        if ((self._batched(Q) and self.path == nv.PATH_AUTO)
+                or self.path in (nv.PATH_UMMA, nv.PATH_UMMA_BF16, nv.PATH_FLASH)) \
                 and self.bank.D % 128 == 0:
             self.bank.ensure_planes()        # batched calls go to the tcgen05 kernels
         s = self._get(Q, normalize_channels > 0)
@@ -240,11 +241,12 @@ class Projector:
         holds denom [Q], gate [Q] (int32), mean [1] and num [Q,D] as device tensors."""
         Q, xf = self._flat_query(x0)
         if (self.group is None and apply and normalize_channels == 0
-                and self.path in (nv.PATH_AUTO, nv.PATH_UMMA if self._batched(Q) else nv.PATH_STREAM)
+                and self.path in (nv.PATH_AUTO, nv.PATH_STREAM, nv.PATH_UMMA, nv.PATH_FLASH)
                 and self._few_launch.get(Q, True)):
-            # one GPU, plain query: the fused sequences (2 launches for Q <= 8, 5 for batched) instead of 6-8
+            # one GPU, plain query: the fused sequences (1 launch one-pass tcgen05, 2 for Q <= 8, 5 two-phase tcgen05)
             b = self.bank
-            use_planes = (self._batched(Q) or self.path == nv.PATH_UMMA) and b.D % 128 == 0
+            use_planes = ((self._batched(Q) and self.path == nv.PATH_AUTO)
+                          or self.path in (nv.PATH_UMMA, nv.PATH_FLASH)) and b.D % 128 == 0
             if use_planes:
                 b.ensure_planes()
             s = self._get(Q, False)
@@ -255,7 +257,7 @@ class Projector:
                 1.0 / (2.0 * float(sigma) ** 2), int(dist_power), float(bank_alpha), float(eps), float(scale),
                 float(gate_threshold if gate_threshold is not None else 0.0), flags,
                 nv.ptr(s.num) if want_num else None, nv.ptr(s.z), nv.ptr(neg), nv.ptr(s.denom), nv.ptr(s.gate),
-                nv.ptr(s.mean), nv.ptr(k_out), nv.ptr(s.ws), s.ws_bytes, nv.current_stream())
+                nv.ptr(s.mean), nv.ptr(k_out), nv.ptr(s.ws), s.ws_bytes, self.path, nv.current_stream())
             if rc == 0:
                 return neg, s
             if rc != -6:

@@ -48,7 +48,7 @@ def _probe_paths(nv, Q, N, D):
     paths = [nv.PATH_GENERIC]
     bank = NegativeBank(torch.zeros(N, D, device="cuda") + 1.0, with_planes=True)
     x = torch.ones(Q, D, device="cuda")
-    for p in (nv.PATH_STREAM, nv.PATH_UMMA):
+    for p in (nv.PATH_STREAM, nv.PATH_UMMA, nv.PATH_FLASH):
         try:
             Projector(bank, path=p).partial_sums(x, 1.0)
             paths.append(p)
@@ -95,6 +95,15 @@ SHAPES = [  # (name, Q, N, C, H, W)
     ("umma-q130", 130, 257, 2, 32, 32),
     ("umma-n129-d128", 16, 129, 2, 8, 8),
     ("umma-n63", 9, 63, 4, 16, 16),
+    # edges of the one-pass tcgen05 path (D = 8192 / 16384): tiles of 64 bank rows (1, 64, 65, 130 rows), one and two
+    # query groups per pass (65, 128 rows), two passes (130 rows), the smaller grid (64 CTAs)
+    ("flash-n1", 16, 1, 4, 64, 64),
+    ("flash-n64", 9, 64, 4, 64, 64),
+    ("flash-n65", 16, 65, 4, 64, 64),
+    ("flash-q65", 65, 130, 4, 64, 64),
+    ("flash-q128", 128, 200, 4, 64, 64),
+    ("flash-q130", 130, 100, 4, 64, 64),
+    ("flash-d8192", 24, 150, 2, 64, 64),
 ]
 
 

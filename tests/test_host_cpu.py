@@ -219,14 +219,17 @@ def test_new_entry_points_validate_arguments(nv):
     assert L.sdn_set_option(nv.OPT_SKIP_NEGLIGIBLE, 1) == 0
     assert L.sdn_set_option(12345, 1) == -4
     assert L.sdn_repel_path(1, 515, 16384, 0, nv.PATH_AUTO) == nv.PATH_STREAM
-    assert L.sdn_repel_path(64, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_UMMA
-    assert L.sdn_repel_path(8, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_UMMA         # FMA-bound for the cluster kernel
+    assert L.sdn_repel_path(64, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_FLASH       # one pass over the bank
+    assert L.sdn_repel_path(128, 30000, 16384, 1, nv.PATH_AUTO) == nv.PATH_FLASH
+    assert L.sdn_repel_path(16, 515, 65536, 1, nv.PATH_AUTO) == nv.PATH_UMMA         # SD3: more d-blocks than SMs
+    assert L.sdn_repel_path(16, 515, 4096, 1, nv.PATH_AUTO) == nv.PATH_UMMA          # too few d-blocks to fill the GPU
+    assert L.sdn_repel_path(8, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_FLASH        # FMA-bound for the cluster kernel
     assert L.sdn_repel_path(8, 515, 16384, 1, nv.PATH_AUTO) == nv.PATH_STREAM
     assert L.sdn_repel_path(4, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_STREAM
     assert L.sdn_repel_path(64, 3000, 16384, 0, nv.PATH_AUTO) == nv.PATH_GENERIC     # no planes: CUDA cores
     assert L.sdn_repel_path(3, 37, 256, 0, nv.PATH_AUTO) == nv.PATH_GENERIC          # D too small for the cluster kernel
     assert L.sdn_conditioning_fused(None, None, None, 1, 4, None, 1, 1.0, 1, 1.0, 0.0, 0.0, 0.0, 0,
-                                    None, None, None, None, None, None, None, None, 0, None) == -1
+                                    None, None, None, None, None, None, None, None, 0, 0, None) == -1
     arr = (C.c_void_p * 2)(None, None)
     assert L.sdn_shard_merge_correct(arr, arr, arr, 0, 9, None, 1, 4, 0.0, 0.0, 0.0, 0, None, None, None, None, None) == -1
     assert L.sdn_bank_build(None, 1, 4, 16, None, None, None, None) == -1

@@ -1,0 +1,84 @@
+"""Ad-hoc probe of the one-pass tcgen05 path (SDN_PATH_FLASH): errors vs the fp64 oracle, the diagnostic record of a
+bounded-wait trap, and CUDA-event timings with L2 flushed.  Each case runs in its own process when --isolate is given
+(a trap kills the CUDA context).
+
+    python tools/gpu_flash_probe.py            # the whole ladder, stops at the first failure
+    python tools/gpu_flash_probe.py Q N [regime sigma time]
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import repellency_oracle as orc                      # noqa: E402
+from safe_denoiser_b200 import _native as nv                     # noqa: E402
+from safe_denoiser_b200.projection import NegativeBank, Projector  # noqa: E402
+
+
+def err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def run(Q, N, regime="near", sigma=3.15, time_it=False, C=4, H=64, W=64):
+    bank4 = orc.synthetic_bank(N, C, H, W)
+    bank = NegativeBank(bank4.cuda(), with_planes=True)
+    x4 = orc.synthetic_queries(bank4, Q, regime)
+    want = orc.closed_form(x4.numpy(), bank4.numpy(), sigma=sigma)
+    x = x4.cuda()
+    for path in (nv.PATH_FLASH,):
+        proj = Projector(bank, path=path)
+        k = torch.zeros(Q, N, device="cuda")
+        try:
+            s = proj.partial_sums(x, sigma, k_out=k)
+            torch.cuda.synchronize()
+        except RuntimeError as e:
+            print(f"Q={Q} N={N} {regime} FAILED: {str(e)[:200]}  diag={nv.debug_read()}", flush=True)
+            raise
+        ek, ez, en = err(k.cpu().numpy(), want["k"]), err(s.z.cpu().numpy(), want["Z"]), err(s.num.cpu().numpy(), want["num"])
+        msg = f"Q={Q} N={N} D={C*H*W} {regime} sigma={sigma} path={path}: err k {ek:.2e} z {ez:.2e} num {en:.2e}"
+        # fused conditioning on the same inputs + run-to-run reproducibility
+        xa, xb = x.clone(), x.clone()
+        proj.correct(xa, sigma, 0.33, 1e-8)
+        proj.correct(xb, sigma, 0.33, 1e-8)
+        torch.cuda.synchronize()
+        wantc = orc.conditioning_fast(x4.numpy(), bank4.numpy(), scale=0.33, sigma=sigma)
+        msg += f" | fused x0 err {err(xa.cpu().numpy(), wantc['x_0_hat']):.2e} bitwise-repeat {bool(torch.equal(xa, xb))}"
+        if time_it:
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            for label, fn in (("partial", lambda: proj.partial_sums(x, sigma)), ("fused", lambda: proj.correct(xa, sigma, 0.33, 1e-8))):
+                ts = []
+                for _ in range(30):
+                    flush.zero_()
+                    _ = flush.sum()
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ts.sort()
+                gb = (N * C * H * W * 4 + N * 4 + 2 * Q * C * H * W * 4) / 1e9
+                med = ts[len(ts) // 2]
+                msg += f" | {label} med {med*1e3:.1f} us min {ts[0]*1e3:.1f} -> {gb/med*1e3:.0f} GB/s"
+        print(msg, flush=True)
+        assert ek <= 1e-3 and ez <= 1e-3 and en <= 1e-3, "outside tolerance"
+
+
+LADDER = [
+    (16, 1), (16, 64), (16, 65), (64, 200), (1, 515), (16, 515, "near", 3.15, 1), (64, 3000, "near", 3.15, 1),
+    (64, 3000, "near", 1.0, 0), (64, 3000, "far", 1.0, 0), (64, 3000, "mid", 1.0, 0), (64, 3000, "x0", 13.15, 0),
+    (65, 130), (128, 3000, "near", 3.15, 1), (130, 257), (128, 30000, "near", 3.15, 1), (64, 30000, "near", 3.15, 1),
+]
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2:
+        a = sys.argv[1:]
+        run(int(a[0]), int(a[1]), a[2] if len(a) > 2 else "near", float(a[3]) if len(a) > 3 else 3.15,
+            bool(int(a[4])) if len(a) > 4 else False)
+    else:
+        for case in LADDER:
+            r = subprocess.run([sys.executable, __file__] + [str(v) for v in case] + (["near", "3.15", "0"] if len(case) == 2 else []),
+                               timeout=600)
+            if r.returncode != 0:
+                print("stopping at", case, flush=True)
+                sys.exit(1)
