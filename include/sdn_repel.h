@@ -93,6 +93,10 @@ int32_t sdn_profile_read(int32_t index, char* name_out, int32_t name_cap, float*
 /* After a kernel of the one-pass path trapped on a bounded wait (CUDA error "unspecified launch failure"), the
  * first words of its host-mapped diagnostic record: {code, CTA, thread, tile, extra}.  Returns 0 when there is none. */
 int32_t sdn_debug_read(uint32_t* words_out, int32_t n);
+/* With SDN_FLASH_TRACE=1 in the environment at the first one-pass call, the kernel records %globaltimer at the hand-offs
+ * of its pipeline: uint64 [128 CTAs][64 tiles][16 events] (1 MiB) of the last launch, copied to host_out.  Returns
+ * the bytes written, 0 when tracing is off or host_out is too small.  (tools/gpu_flash_trace.py prints the stage latencies.) */
+size_t sdn_debug_trace_read(void* host_out, size_t bytes);
 
 /* ---- bank -------------------------------------------------------------------------------
  * Derived data of the proj_ref tensor, computed once at load (fast.py:109-111 loads the tensor;

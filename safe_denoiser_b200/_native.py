@@ -23,6 +23,7 @@ SIGNATURES = {
     "sdn_launch_count": (C.c_uint64, []),
     "sdn_set_option": (C.c_int, [_i32, _i32]),
     "sdn_debug_read": (_i32, [C.POINTER(C.c_uint32), _i32]),
+    "sdn_debug_trace_read": (_sz, [_p, _sz]),
     "sdn_profile_enable": (None, [_i32]),
     "sdn_profile_read": (_i32, [_i32, C.c_char_p, _i32, C.POINTER(C.c_float)]),
     "sdn_bank_prepare": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),

@@ -68,5 +68,6 @@ int flash_run(const void* planes, const float* sqnorm, int64_t N, int64_t D, con
               float inv_two_sigma_sq, int power, float alpha, float* num_out, float* z_out, float* k_out,
               const FlashEpi* epi, cudaStream_t st);
 int flash_diag_read(uint32_t* out, int n);
+size_t flash_trace_read(void* host_out, size_t bytes);
 
 }  // namespace sdn
