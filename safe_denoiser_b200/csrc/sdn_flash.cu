@@ -1,34 +1,36 @@
 // One-pass "flash-repellency" for batched calls: the bank is read from HBM exactly once.
 //
 // Replaces repellency_methods_fast.py:249-250 (cdist + the [Q,N,D+1] broadcast) for 8 < Q <= 128 query rows per pass.
-// The two-phase tcgen05 path (sdn_umma.cu) streams the bank twice because the weights of a bank row need its dot
-// product over ALL of D before the row can be accumulated.  Here the row tile stays in shared memory between the
-// two contractions instead:
+// The two-phase tcgen05 path (sdn_umma.cu) streams the bank twice from HBM because the weights of a bank row need its
+// dot product over ALL of D before the row can be accumulated, and its two kernels are a whole bank apart.  Here both
+// contractions run in ONE persistent kernel, a few tiles apart, so that the second read of a tile hits the L2:
 //
 //   grid   = D / 128 CTAs (one per SM, clusters of 4); CTA j owns the d-slice [128 j, 128 j + 128) of every bank row
 //            and keeps  X[:, slice]  (bf16 hi/lo, tcgen05 A operand)  and  num[:, slice]  (fp32 accumulator) in
 //            TENSOR MEMORY for the whole kernel;
-//   tile   = 64 bank rows x the slice, hi and lo planes (32 KiB) -> one shared-memory stage filled by TMA;
-//   phase A  S_j[q][i] = sum_{d in slice} X[q][d] bank[i][d]      tcgen05.mma, A = X (TMEM), B = tile (K-major)
+//   tile   = 64 bank rows x the slice, hi and lo planes (32 KiB) = one shared-memory stage filled by TMA;
+//   phase A  S_j[q][i] = sum_{d in slice} X[q][d] bank[i][d]      tcgen05.mma, A = X (TMEM), B = tile (K-major);
+//            the tile is loaded with an L2 evict_last policy and its stage is released at once;
 //   reduce   S[q][i] = sum_j S_j[q][i] over the D/128 CTAs:
 //              level 1  inside the cluster over distributed shared memory (st.async + mbarrier complete_tx):
 //                       CTA c of a cluster receives and sums rows [16c, 16c+16) of the tile;
 //              level 2  the cluster partials go through L2 as self-validating 16-byte lines {v, tag, v, tag}
 //                       (no fence, no flag) to "jobs" of 4 rows x 64 queries dealt round-robin over ALL CTAs: the
 //                       job's CTA sums the 32 cluster partials in cluster order, computes k = exp(-dist / 2 sigma^2)
-//                       and publishes the weights into [Q][64] (+ one release flag per warp);
+//                       and publishes the weights as fp32 words whose low 4 mantissa bits carry the tile's sequence
+//                       number (again no fence, no flag: every word validates itself);
 //   phase B  num[q][slice] += sum_i k[q][i] bank[i][slice]        tcgen05.mma, A = weights (bf16 hi/lo written to
-//            TMEM by tcgen05.st), B = THE SAME shared-memory tile viewed MN-major; its commit frees the stage.
+//            TMEM by tcgen05.st), B = the tile viewed MN-major, loaded AGAIN by TMA (evict_first: it is not needed
+//            any more) when the tile's weights show up -- a hit in the 126 MB L2 as long as the exchange lags the
+//            stream by less than the L2 (a resident-tile variant was measured first: with 6 stages per SM the
+//            ~15 us round trip of the exchange capped it at 1.3 TB/s).
 //
 // Every sum has a fixed order (CTA rank, cluster index, row index): results are bit-reproducible run to run.
-// A stage lives from its TMA issue to the commit of phase B, i.e. through the cross-CTA reduction (a few us), so
-// the achievable HBM rate is (stages x 32 KiB x CTAs) / that latency; everything in the exchange is built to keep
-// it short (no fences on the fan-in, DSMEM for the first 8:1).
 //
-// Warp roles (16 warps, 1 CTA per SM): 0 TMA producer | 1 MMA issuer (event loop over "phase A of tile ta ready" /
-// "weights of tile tb ready") | 4-7 phase-A drain: TMEM -> registers -> DSMEM scatter, then the level-1 sum |
-// 8-11 weights: global -> bf16 hi/lo -> TMEM, z_q, and the final epilogue | 12-15 tile owner: ||x||^2, level-2 sum,
-// exp, publish.
+// Warp roles (16 warps, 1 CTA per SM): 0 TMA producer phase A | 1 MMA issuer (event loop over "tile ta loaded" /
+// "weights and tile tb ready") | 2-3 level-1 sum | 4-7 phase-A drain: TMEM -> registers -> staging -> bulk DSMEM copies |
+// 8-11 weights: global -> bf16 hi/lo -> TMEM (warp 8 also issues the second TMA read of the tile), z_q, and the final
+// epilogue | 12-15 level-2 jobs: ||x||^2, sum over clusters, exp, publish.
 #include <cuda.h>
 
 #include <algorithm>
@@ -48,28 +50,38 @@ constexpr int kFCS = 4;                 // CTAs per cluster (this pool's B200s c
 constexpr int kFRowsPerOwner = kFR / kFCS;   // rows of a tile that CTA c of a cluster reduces at level 1
 constexpr int kFJobRows = 4;            // rows of a tile per level-2 job (one float4 per query row)
 constexpr int kFJobsPerGroup = kFR / kFJobRows;   // 16 jobs per tile and group of 64 query rows
-constexpr int kFRing = 8;               // tiles in flight in the global exchange rings (> stages)
+constexpr int kFRing = 32;              // slots of the global exchange rings: phase A runs at most kFWindow < kFRing tiles ahead of phase B
+constexpr int kFWindow = 12;            // tiles between the two reads of the bank: 12 x 4 MiB stay in the 126 MB L2 (and < the 16 tiles between two units of a level-2 worker)
 constexpr int kFThreads = 512;
 constexpr int kFMaxCtas = 128;
 constexpr int kFMaxClusters = kFMaxCtas / kFCS;
 constexpr uint32_t kFStageBytes = 2u * kFR * kFDS * 2u;   // hi + lo tiles of [64 rows][128 d] bf16 = 32 KiB
 constexpr uint32_t kFTmemCols = 512;
-constexpr uint32_t kFColX = 0;          // X operand: G = 1: 64 columns (stacked hi|lo rows); G = 2: hi 64 | lo 64
-constexpr uint32_t kFColS = 128;        // S accumulators, 2 x 64 columns
-constexpr uint32_t kFColP = 256;        // weight operands, 2 x 64 columns (G = 2: hi 32 | lo 32)
-constexpr uint32_t kFColAcc = 384;      // num accumulator, 128 columns
 constexpr uint32_t kFSpinLimit = 1u << 24;
 
 template <int G>
 struct FCfg {
   static constexpr int kQ = 64 * G;                                   // query rows per pass
-  static constexpr int kStages = G == 1 ? 6 : 5;
-  static constexpr int kSliceFloats = kQ * kFRowsPerOwner;            // one (tile, level-1 owner) slice: [kQ][rows per owner]
+  static constexpr int kSA = 2;                                       // stages of phase A (HBM stream; released as soon as the MMAs have read them)
+  static constexpr int kSB = 2;                                       // stages of phase B (second read, from L2)
+  static constexpr int kStages = kSA + kSB;
+  static constexpr int kSlots = 3;                                    // level-1 units in flight in the cluster (receive slots = staging buffers)
+  static constexpr int kSBuf = G == 1 ? 4 : 2;                        // S accumulators in tensor memory
+  // level-1 unit = (tile, group of 64 query rows); a slice = what one CTA of the cluster owns of a unit
+  static constexpr int kSliceFloats = 64 * kFRowsPerOwner;            // [sub 4][q 64][4 rows]
   static constexpr int kSliceVec = kSliceFloats / 4 / 128;            // float4 per thread of the level-1 sum
-  static constexpr uint32_t kRbufSlotBytes = (uint32_t)kFCS * kSliceFloats * 4;   // [src][kQ][rows per owner]
+  static constexpr uint32_t kRbufSlotBytes = (uint32_t)kFCS * kSliceFloats * 4;   // [src or owner][slice]
   static constexpr int kJobs = kFJobsPerGroup * G;                    // level-2 jobs per tile
   static constexpr int kXStages = (kQ * 132 * 4 + (int)kFStageBytes - 1) / (int)kFStageBytes;   // stages the query staging covers
-  static constexpr uint32_t kSmemBytes = kStages * kFStageBytes + 2 * kRbufSlotBytes + 1024 /*align*/ + 1536 /*barriers, xsq*/;
+  static constexpr int kXOverA = kXStages > kSB ? kXStages - kSB : 0;                           // ... of which phase-A stages
+  // tensor-memory columns: X | S accumulators | weight operands | num accumulator
+  static constexpr uint32_t kColX = 0;
+  static constexpr uint32_t kColS = 64 * G;
+  static constexpr uint32_t kColP = kColS + 64 * kSBuf;
+  static constexpr uint32_t kPStride = 32 * G;                        // columns of one weight operand buffer (G = 2: hi 32 | lo 32)
+  static constexpr uint32_t kColAcc = 384;
+  static_assert(kColP + 2 * kPStride <= kColAcc, "tensor memory layout");
+  static constexpr uint32_t kSmemBytes = kStages * kFStageBytes + 2 * kSlots * kRbufSlotBytes + 1024 /*align*/ + 1536 /*barriers, xsq*/;
   static_assert(kSmemBytes <= 232448, "more than 227 KiB of shared memory");
 };
 
@@ -88,7 +100,8 @@ struct FlashArena {
 struct FlashArgs {
   const float* xq;      // [Q][D] query the distances are taken on
   const float* sqnorm;  // [N]
-  int Q, N, ntiles, nclusters;
+  int Q, N, ntiles, nclusters, window;
+  unsigned mma_sleep, poll_sleep;     // back-off of the polling loops (ns)
   int64_t D;
   float inv2s2, alpha; int power;
   float* num_out;       // [Q][D] or null
@@ -154,15 +167,24 @@ __device__ __forceinline__ uint32_t f_pack_bf16(float lo_elem, float hi_elem) {
 }
 __device__ __forceinline__ float f_bf16_hi(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+// TMA tile load with an L2 eviction policy (phase A: evict_last, the tile is read again a few tiles later;
+// phase B: evict_first, it is never needed again)
+__device__ __forceinline__ void f_tma_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(u_smem(dst)), "l"(map), "r"(u_smem(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+
 struct FSmem {
-  uint8_t* stages;
-  float* rbuf;          // [2][kFCS][slice floats]
-  uint64_t* full; uint64_t* empty;        // [stages]
-  uint64_t* sfull; uint64_t* sempty;      // [2] S accumulators
+  uint8_t* stages;      // [kSA phase-A stages | kSB phase-B stages] x 32 KiB
+  float* rbuf;          // [kSlots][kFCS][slice floats] receive slots, then [kSlots][kFCS][slice floats] send staging
+  uint64_t* afull; uint64_t* aempty;      // [kSA]
+  uint64_t* bfull; uint64_t* bempty;      // [kSB]
+  uint64_t* bgo;                          // [4] weights of tile u seen: its second load may start
+  uint64_t* sfull; uint64_t* sempty;      // [kSBuf] S accumulators
   uint64_t* pfull; uint64_t* pempty;      // [2] weight operands
-  uint64_t* rfull; uint64_t* rfree;       // [2] level-1 receive slots
+  uint64_t* rfull; uint64_t* rfree;       // [kSlots] level-1 receive slots
   uint64_t* xfull; uint64_t* accfull;     // [1]
-  uint64_t* wready;                       // [kFRing] weights of tile t published (signalled by the cluster's rank-0 CTA)
   uint64_t* xload;                        // [4] query rows of one phase-A warp staged in shared memory
   uint32_t* tmem_base;
   float* xsq;           // [128]
@@ -176,21 +198,23 @@ __device__ __forceinline__ FSmem f_carve(unsigned char* raw) {
   const uintptr_t a = (reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023;
   s.stages = reinterpret_cast<uint8_t*>(a);
   s.rbuf = reinterpret_cast<float*>(s.stages + (size_t)C::kStages * kFStageBytes);
-  uint64_t* b = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s.rbuf) + 2 * C::kRbufSlotBytes);
-  s.full = b; b += 8;
-  s.empty = b; b += 8;
-  s.sfull = b; b += 2;
-  s.sempty = b; b += 2;
+  uint64_t* b = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s.rbuf) + 2 * C::kSlots * C::kRbufSlotBytes);
+  s.afull = b; b += 4;
+  s.aempty = b; b += 4;
+  s.bfull = b; b += 4;
+  s.bempty = b; b += 4;
+  s.bgo = b; b += 4;
+  s.sfull = b; b += 4;
+  s.sempty = b; b += 4;
   s.pfull = b; b += 2;
   s.pempty = b; b += 2;
-  s.rfull = b; b += 2;
-  s.rfree = b; b += 2;
+  s.rfull = b; b += 4;
+  s.rfree = b; b += 4;
   s.xfull = b; b += 1;
   s.accfull = b; b += 1;
-  s.wready = b; b += kFRing;
   s.xload = b; b += 4;
   s.tmem_base = reinterpret_cast<uint32_t*>(b); b += 1;
-  s.xsq = reinterpret_cast<float*>(b);          // 43 x 8 = 344 bytes of barriers so far
+  s.xsq = reinterpret_cast<float*>(b);          // 51 x 8 = 408 bytes of barriers so far
   s.xsq_half = s.xsq + 128;
   return s;
 }
@@ -218,18 +242,17 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
   float* const estage = reinterpret_cast<float*>(sm.stages);      // epilogue staging: every stage is free by then
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      u_mbar_init(&sm.sfull[b], 1); u_mbar_init(&sm.sempty[b], 4);
-      u_mbar_init(&sm.pfull[b], 4); u_mbar_init(&sm.pempty[b], 1);
-      u_mbar_init(&sm.rfull[b], 1); u_mbar_init(&sm.rfree[b], kFCS * 4);
-    }
+    for (int s = 0; s < C::kSA; ++s) { u_mbar_init(&sm.afull[s], 1); u_mbar_init(&sm.aempty[s], 1); }
+    for (int s = 0; s < C::kSB; ++s) { u_mbar_init(&sm.bfull[s], 1); u_mbar_init(&sm.bempty[s], 1); }
+    for (int s = 0; s < 4; ++s) u_mbar_init(&sm.bgo[s], 1);
+    for (int b = 0; b < C::kSBuf; ++b) { u_mbar_init(&sm.sfull[b], 1); u_mbar_init(&sm.sempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.pfull[b], 4); u_mbar_init(&sm.pempty[b], 1); }
+    for (int b = 0; b < C::kSlots; ++b) { u_mbar_init(&sm.rfull[b], 1); u_mbar_init(&sm.rfree[b], kFCS * 2); }
     u_mbar_init(sm.xfull, 4); u_mbar_init(sm.accfull, 1);
     for (int w = 0; w < 4; ++w) u_mbar_init(&sm.xload[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // arm the two level-1 receive slots for their first tiles
-    u_mbar_expect_tx(&sm.rfull[0], C::kRbufSlotBytes);
-    u_mbar_expect_tx(&sm.rfull[1], C::kRbufSlotBytes);
+    // arm the level-1 receive slots for their first tiles
+    for (int b = 0; b < C::kSlots; ++b) u_mbar_expect_tx(&sm.rfull[b], C::kRbufSlotBytes);
     u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
     if (cta == 0 && a.epi.zero_mean && a.epi.mean_out) { *a.epi.mean_out = 0.f; __threadfence(); }
   }
@@ -242,33 +265,38 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
   u_fence_after();
   const uint32_t tmem = *sm.tmem_base;
 
-  auto load_stage = [&](int t) {
-    const int s = t % C::kStages;
-    uint8_t* st = sm.stages + (size_t)s * kFStageBytes;
-    u_mbar_expect_tx(&sm.full[s], kFStageBytes);
+  uint64_t pol_keep, pol_drop;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
+  // tile t of this CTA's slice: hi and lo planes, two boxes of [64 rows][64 d] each
+  auto load_tile = [&](uint8_t* st, uint64_t* bar, int t, uint64_t policy) {
+    u_mbar_expect_tx(bar, kFStageBytes);
     const int r0 = t * kFR;
+    f_tma_2d_hint(st, &tm_hi, d0, r0, bar, policy);
+    f_tma_2d_hint(st + 8192, &tm_hi, d0 + 64, r0, bar, policy);
+    f_tma_2d_hint(st + 16384, &tm_lo, d0, r0, bar, policy);
+    f_tma_2d_hint(st + 24576, &tm_lo, d0 + 64, r0, bar, policy);
+  };
+  auto load_a = [&](int t) {
     f_trace(a, t, 0);
-    u_tma_2d(st, &tm_hi, d0, r0, &sm.full[s]);
-    u_tma_2d(st + 8192, &tm_hi, d0 + 64, r0, &sm.full[s]);
-    u_tma_2d(st + 16384, &tm_lo, d0, r0, &sm.full[s]);
-    u_tma_2d(st + 24576, &tm_lo, d0 + 64, r0, &sm.full[s]);
+    load_tile(sm.stages + (size_t)(t % C::kSA) * kFStageBytes, &sm.afull[t % C::kSA], t, pol_keep);
   };
   // the first stages depend on nothing but this CTA's own barriers: start the stream before the cluster barrier
-  const int npre = min(ntiles, C::kStages - C::kXStages);
+  const int npre = min(ntiles, C::kSA - C::kXOverA);
   if (threadIdx.x == 0)
-    for (int t = 0; t < npre; ++t) load_stage(t);
+    for (int t = 0; t < npre; ++t) load_a(t);
 
   // every CTA of the cluster has initialised its barriers before any peer stores into its shared memory
   u_cluster_arrive();
   u_cluster_wait();
 
   if (warp == 0) {
-    // ============================================================ TMA producer
+    // ============================================================ TMA producer, phase A (HBM stream)
     if (lane == 0) {
-      if (ntiles > npre) f_wait(a, sm.xfull, 0, 0x110, 0);      // the query staging area becomes pipeline stages
+      if (C::kXOverA > 0 && ntiles > npre) f_wait(a, sm.xfull, 0, 0x110, 0);      // the query staging area becomes a stage
       for (int t = npre; t < ntiles; ++t) {
-        if (t >= C::kStages) f_wait(a, &sm.empty[t % C::kStages], (uint32_t)(((t / C::kStages) + 1) & 1), 0x100, t);
-        load_stage(t);
+        if (t >= C::kSA) f_wait(a, &sm.aempty[t % C::kSA], (uint32_t)(((t / C::kSA) + 1) & 1), 0x100, t);
+        load_a(t);
       }
     }
   } else if (warp == 1) {
@@ -282,13 +310,14 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
       uint32_t idle = 0;
       while (tb < ntiles) {
         bool did = false;
-        if (tb < ta && u_mbar_test(&sm.pfull[tb & 1], (uint32_t)((tb >> 1) & 1))) {
+        if (tb < ta && u_mbar_test(&sm.pfull[tb & 1], (uint32_t)((tb >> 1) & 1)) &&
+            u_mbar_test(&sm.bfull[tb % C::kSB], (uint32_t)((tb / C::kSB) & 1))) {
           // ---- phase B of tile tb: 4 K steps of 16 bank rows
           u_fence_after();
           f_trace(a, tb, 8);
-          const uint32_t base = u_smem(sm.stages + (size_t)(tb % C::kStages) * kFStageBytes);
-          const uint32_t acc = tmem + kFColAcc;
-          const uint32_t pb = tmem + kFColP + (uint32_t)(tb & 1) * 64;
+          const uint32_t base = u_smem(sm.stages + (size_t)(C::kSA + tb % C::kSB) * kFStageBytes);
+          const uint32_t acc = tmem + C::kColAcc;
+          const uint32_t pb = tmem + C::kColP + (uint32_t)(tb & 1) * C::kPStride;
 #pragma unroll
           for (int kk = 0; kk < kFR / 16; ++kk) {
             const uint64_t bh = u_desc(base + kk * 2048, 8192, 1024);
@@ -298,37 +327,39 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
             u_mma_ts(acc, pb + kk * 8, bl, idB, 1u);
             if constexpr (G == 2) u_mma_ts(acc, pb + 32 + kk * 8, bh, idB, 1u);
           }
-          u_commit(&sm.empty[tb % C::kStages]);
+          u_commit(&sm.bempty[tb % C::kSB]);
           u_commit(&sm.pempty[tb & 1]);
           if (tb == ntiles - 1) u_commit(sm.accfull);
           ++tb;
           did = true;
         }
-        if (ta < ntiles && u_mbar_test(&sm.full[ta % C::kStages], (uint32_t)((ta / C::kStages) & 1)) &&
-            (ta < 2 || u_mbar_test(&sm.sempty[ta & 1], (uint32_t)(((ta >> 1) + 1) & 1)))) {
-          // ---- phase A of tile ta: 8 K steps of 16 d
+        // phase A stays within `window` tiles of phase B: the exchange rings (kFRing slots) are reused safely and the
+        // tiles waiting for their second read fit in the L2
+        if (ta < ntiles && ta - tb < a.window && u_mbar_test(&sm.afull[ta % C::kSA], (uint32_t)((ta / C::kSA) & 1)) &&
+            (ta < C::kSBuf || u_mbar_test(&sm.sempty[ta % C::kSBuf], (uint32_t)(((ta / C::kSBuf) + 1) & 1)))) {
+          // ---- phase A of tile ta: 8 K steps of 16 d; its stage is free again as soon as these MMAs have read it
           u_fence_after();
           f_trace(a, ta, 1);
-          const uint32_t base = u_smem(sm.stages + (size_t)(ta % C::kStages) * kFStageBytes);
-          const uint32_t acc = tmem + kFColS + (uint32_t)(ta & 1) * 64;
+          const uint32_t base = u_smem(sm.stages + (size_t)(ta % C::kSA) * kFStageBytes);
+          const uint32_t acc = tmem + C::kColS + (uint32_t)(ta % C::kSBuf) * 64;
 #pragma unroll
           for (int kk = 0; kk < kFDS / 16; ++kk) {
             const uint32_t off = (uint32_t)(kk >> 2) * 8192 + (uint32_t)(kk & 3) * 32;
             const uint64_t bh = u_desc(base + off, 16, 1024);
             const uint64_t bl = u_desc(base + 16384 + off, 16, 1024);
-            u_mma_ts(acc, tmem + kFColX + kk * 8, bh, idA, kk > 0 ? 1u : 0u);
-            u_mma_ts(acc, tmem + kFColX + kk * 8, bl, idA, 1u);
-            if constexpr (G == 2) u_mma_ts(acc, tmem + kFColX + 64 + kk * 8, bh, idA, 1u);
+            u_mma_ts(acc, tmem + C::kColX + kk * 8, bh, idA, kk > 0 ? 1u : 0u);
+            u_mma_ts(acc, tmem + C::kColX + kk * 8, bl, idA, 1u);
+            if constexpr (G == 2) u_mma_ts(acc, tmem + C::kColX + 64 + kk * 8, bh, idA, 1u);
           }
-          u_commit(&sm.sfull[ta & 1]);
+          u_commit(&sm.sfull[ta % C::kSBuf]);
+          u_commit(&sm.aempty[ta % C::kSA]);
           ++ta;
           did = true;
         }
         if (did) idle = 0;
         else {
-          // nothing ready: sleep in hardware on the barrier most likely to fire next instead of spinning on probes
-          if (tb < ta) u_mbar_try(&sm.pfull[tb & 1], (uint32_t)((tb >> 1) & 1), 200);
-          else if (ta < ntiles) u_mbar_try(&sm.full[ta % C::kStages], (uint32_t)((ta / C::kStages) & 1), 200);
+          // this thread shares its scheduler with a drain, a weights and a level-2 warp: do not spin at full rate
+          if (a.mma_sleep) __nanosleep(a.mma_sleep);
           if (++idle > kFSpinLimit) f_timeout(a, 0x210, (uint32_t)ta, (uint32_t)tb);
         }
       }
@@ -380,10 +411,10 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
           uint32_t sel[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) sel[j] = part ? lo[j] : hi[j];
-          u_tmem_st16(tlane + kFColX + c4 * 16, sel);
+          u_tmem_st16(tlane + C::kColX + c4 * 16, sel);
         } else {
-          u_tmem_st16(tlane + kFColX + c4 * 16, hi);
-          u_tmem_st16(tlane + kFColX + 64 + c4 * 16, lo);
+          u_tmem_st16(tlane + C::kColX + c4 * 16, hi);
+          u_tmem_st16(tlane + C::kColX + 64 + c4 * 16, lo);
         }
       }
       u_tmem_st_wait();
@@ -394,114 +425,119 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
       if (lane == 0) u_mbar_arrive(sm.xfull);
     }
 
-    // Level-1 slice of CTA c of the cluster: rows [16c, 16c+16) of the tile for all query rows, stored as
-    // [sub 4][q kQ][4 rows]; float4 index = sub * kQ + q.
-    const uint32_t rbuf_s = u_smem(sm.rbuf);
-    auto l1sum = [&](int u) {
-      const int slot = u & 1;
-      f_wait(a, &sm.rfull[slot], (uint32_t)((u >> 1) & 1), 0x300, u);
-      if (warp == 4 && lane == 0 && u + 2 < ntiles) u_mbar_expect_tx(&sm.rfull[slot], C::kRbufSlotBytes);   // next use
-      if (warp == 4 && lane == 0) f_trace(a, u, 4);
-      const uint32_t tag = epoch0 + (uint32_t)u;            // the tile's sequence number (gap-free over launches)
+    // ---- level 1, per unit u = (tile t, group g of 64 query rows):
+    //   drain   S(t) rows of the group: TMEM -> registers -> send staging in shared memory, laid out per owner CTA
+    //           [owner 4][sub 4][q 64][4 rows] (the owner of rows [16c, 16c+16) of the tile is CTA c of the cluster);
+    //   send    one 4 KiB bulk copy (cp.async.bulk shared::cta -> shared::cluster) per owner: ONE transaction on the
+    //           owner's mbarrier instead of 256 (16-byte st.async from registers kept that barrier busy for 2.6 us a tile);
+    //   sum     the previous unit's slices of this CTA over the 4 senders, published as LL lines for the level-2 jobs.
+    // Phase A runs several tiles ahead of the exchange, so this loop never waits for HBM.
+    float* const stg = sm.rbuf + (size_t)C::kSlots * (C::kRbufSlotBytes / 4);
+    const int myg = G == 1 ? 0 : (L >> 6);
+    const int q64 = G == 1 ? q : (L & 63);
+    const int nunits = ntiles * G;
+#pragma unroll 1
+    for (int u = 0; u < nunits; ++u) {
+      const int t = u / G, g = u - t * G;
+      const int sb = u % C::kSlots;
+      if (warp == 4 && lane == 0) f_trace(a, t, 12);
+      // the staging buffer and the owners' receive slot are free once every owner has summed unit u - kSlots
+      if (u >= C::kSlots) f_wait_cluster(a, &sm.rfree[sb], (uint32_t)(((u / C::kSlots) + 1) & 1), 0x320, u);
+      if (warp == 4 && lane == 0) f_trace(a, t, 13);
+      float* sbuf = stg + (size_t)sb * (C::kRbufSlotBytes / 4);
+      if (G == 1 || g == myg) {
+        const int b = t % C::kSBuf;
+        f_wait(a, &sm.sfull[b], (uint32_t)((t / C::kSBuf) & 1), 0x310, t);
+        u_fence_after();
+        if (warp == 4 && lane == 0) f_trace(a, t, 2);
+        uint32_t r0[32], r1[32];
+        u_tmem_ld32_nowait(tlane + C::kColS + (uint32_t)b * 64, r0);
+        u_tmem_ld32_nowait(tlane + C::kColS + (uint32_t)b * 64 + 32, r1);
+        u_tmem_ld_wait();
+        u_fence_before();
+        __syncwarp();
+        if (lane == 0) u_mbar_arrive(&sm.sempty[b]);
+        constexpr int kSubs = kFRowsPerOwner / 4;
+        if constexpr (G == 1) {
+          // lanes l and l+16 hold the hi-part and lo-part rows of the same query: add them, then each stages one half
+          constexpr int kOwnersPerHalf = 32 / kFRowsPerOwner;
+#pragma unroll
+          for (int oo = 0; oo < kOwnersPerHalf; ++oo) {
+#pragma unroll
+            for (int v = 0; v < kSubs; ++v) {
+              float4 o4;
+              float* o = &o4.x;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = oo * kFRowsPerOwner + 4 * v + e;
+                const float v0 = __uint_as_float(r0[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r0[j]), 16);
+                const float v1 = __uint_as_float(r1[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r1[j]), 16);
+                o[e] = part ? v1 : v0;
+              }
+              const int owner = part * kOwnersPerHalf + oo;
+              *reinterpret_cast<float4*>(sbuf + ((size_t)(owner * kSubs + v) * 64 + q64) * 4) = o4;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int oo = 0; oo < kFCS; ++oo) {
+#pragma unroll
+            for (int v = 0; v < kSubs; ++v) {
+              const int e = oo * kFRowsPerOwner + 4 * v;       // row of the tile, compile-time
+              const uint32_t* r = e < 32 ? r0 : r1;
+              const int o = e & 31;
+              *reinterpret_cast<float4*>(sbuf + ((size_t)(oo * kSubs + v) * 64 + q64) * 4) =
+                  make_float4(__uint_as_float(r[o]), __uint_as_float(r[o + 1]), __uint_as_float(r[o + 2]), __uint_as_float(r[o + 3]));
+            }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the bulk copies read what the threads wrote
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      if (warp == 4 && lane == 0) f_trace(a, t, 14);
+      if (warp == 4 && lane < kFCS) {
+        const uint32_t src = u_smem(sbuf + (size_t)lane * C::kSliceFloats);
+        const uint32_t dst = u_mapa(u_smem(sm.rbuf + (size_t)sb * (C::kRbufSlotBytes / 4) + (size_t)crank * C::kSliceFloats), (uint32_t)lane);
+        const uint32_t rbar = u_mapa(u_smem(&sm.rfull[sb]), (uint32_t)lane);
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "r"(src), "r"(C::kSliceFloats * 4), "r"(rbar) : "memory");
+      }
+      if (warp == 4 && lane == 0) f_trace(a, t, 3);
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ============================================================ level-1 sum: the rows this CTA owns, over the cluster
+    const int lt = (warp - 2) * 32 + lane;            // 0..63
+    const int nunits = ntiles * G;
+#pragma unroll 1
+    for (int v = 0; v < nunits; ++v) {
+      const int t = v / G, g = v - t * G;
+      const int slot = v % C::kSlots;
+      f_wait_cluster(a, &sm.rfull[slot], (uint32_t)((v / C::kSlots) & 1), 0x300, v);
+      if (warp == 2 && lane == 0 && v + C::kSlots < nunits) u_mbar_expect_tx(&sm.rfull[slot], C::kRbufSlotBytes);   // next use
+      if (warp == 2 && lane == 0) f_trace(a, t, 4);
+      const uint32_t tag = epoch0 + (uint32_t)t;            // the tile's sequence number (gap-free over launches)
       const float* rb = sm.rbuf + (size_t)slot * (C::kRbufSlotBytes / 4);
       // cluster partial as LL lines, laid out per level-2 job: [job 32][q 64][2 lines of 2 rows]
       uint8_t* dst = a.ar.part_ll + ((size_t)(tag % kFRing) * kFMaxClusters + cluster) * (size_t)(32 * 2048);
 #pragma unroll
-      for (int f = 0; f < C::kSliceVec; ++f) {
-        const int idx4 = L + 128 * f;
-        const int sub = idx4 / C::kQ, qq = idx4 - sub * C::kQ;
+      for (int f = 0; f < C::kSliceFloats / 4 / 64; ++f) {
+        const int idx4 = lt + 64 * f;
+        const int sub = idx4 >> 6, qq = idx4 & 63;
         float4 s4 = *reinterpret_cast<const float4*>(rb + (size_t)idx4 * 4);
 #pragma unroll
         for (int src = 1; src < kFCS; ++src) {
           const float4 p = *reinterpret_cast<const float4*>(rb + (size_t)src * C::kSliceFloats + (size_t)idx4 * 4);
           s4.x += p.x; s4.y += p.y; s4.z += p.z; s4.w += p.w;
         }
-        const int jj = (qq >> 6) * kFJobsPerGroup + (int)crank * (kFRowsPerOwner / kFJobRows) + sub;
-        uint8_t* o = dst + (size_t)jj * 2048 + (size_t)(qq & 63) * 32;
+        const int jj = g * kFJobsPerGroup + (int)crank * (kFRowsPerOwner / kFJobRows) + sub;
+        uint8_t* o = dst + (size_t)jj * 2048 + (size_t)qq * 32;
         u_ll_store(o, s4.x, s4.y, tag);
         u_ll_store(o + 16, s4.z, s4.w, tag);
       }
-      if (warp == 4 && lane == 0) f_trace(a, u, 5);
-      // the slot may be refilled once every warp of every owner has read it
+      if (warp == 2 && lane == 0) f_trace(a, t, 5);
+      // the slot may be refilled (and the senders' staging rewritten) once both warps of every owner have read it
       __syncwarp();
       if (lane < kFCS) u_mbar_arrive_remote(u_mapa(u_smem(&sm.rfree[slot]), (uint32_t)lane));
-    };
-    // drain S(td) -> DSMEM scatter, and the level-1 sum of tile ts as soon as its slot is complete: an event loop per
-    // warp (lane 0 probes, the warp follows), older tile first -- a sum must not wait behind the next tile's HBM data
-    auto drain = [&](int t) {
-      const int b = t & 1;
-      f_wait(a, &sm.sfull[b], (uint32_t)((t >> 1) & 1), 0x310, t);
-      u_fence_after();
-      if (warp == 4 && lane == 0) f_trace(a, t, 2);
-      uint32_t r0[32], r1[32];
-      u_tmem_ld32_nowait(tlane + kFColS + (uint32_t)b * 64, r0);
-      u_tmem_ld32_nowait(tlane + kFColS + (uint32_t)b * 64 + 32, r1);
-      u_tmem_ld_wait();
-      u_fence_before();
-      __syncwarp();
-      if (lane == 0) u_mbar_arrive(&sm.sempty[b]);
-      const int slot = t & 1;
-      if (t >= 2) f_wait(a, &sm.rfree[slot], (uint32_t)(((t >> 1) + 1) & 1), 0x320, t);   // (probed complete by lane 0)
-      // address of (sub 0, q) of this sender's slice in the owner's slot; sub s is kQ * 16 bytes further
-      const uint32_t my_off = ((uint32_t)slot * (C::kRbufSlotBytes / 4) + crank * (uint32_t)C::kSliceFloats + (uint32_t)q * 4u) * 4u;
-      const uint32_t bar_local = u_smem(&sm.rfull[slot]);
-      constexpr int kSubs = kFRowsPerOwner / 4;
-      if constexpr (G == 1) {
-        // lanes l and l+16 hold the hi-part and lo-part rows of the same query: add them, then each sends one half
-        float s[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v0 = __uint_as_float(r0[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r0[j]), 16);
-          const float v1 = __uint_as_float(r1[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r1[j]), 16);
-          s[j] = part ? v1 : v0;
-        }
-        constexpr int kOwnersPerHalf = 32 / kFRowsPerOwner;
-#pragma unroll
-        for (int oo = 0; oo < kOwnersPerHalf; ++oo) {
-          const uint32_t owner = (uint32_t)(part * kOwnersPerHalf + oo);
-          const uint32_t ra = u_mapa(rbuf_s + my_off, owner), rbar = u_mapa(bar_local, owner);
-#pragma unroll
-          for (int v = 0; v < kSubs; ++v) {
-            const int e = oo * kFRowsPerOwner + 4 * v;
-            u_st_async_v4(ra + (uint32_t)v * (C::kQ * 16), rbar, s[e], s[e + 1], s[e + 2], s[e + 3]);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int oo = 0; oo < kFCS; ++oo) {
-          const uint32_t ra = u_mapa(rbuf_s + my_off, (uint32_t)oo), rbar = u_mapa(bar_local, (uint32_t)oo);
-#pragma unroll
-          for (int v = 0; v < kSubs; ++v) {
-            const int e = oo * kFRowsPerOwner + 4 * v;       // row of the tile, compile-time
-            const uint32_t* r = e < 32 ? r0 : r1;
-            const int o = e & 31;
-            u_st_async_v4(ra + (uint32_t)v * (C::kQ * 16), rbar, __uint_as_float(r[o]), __uint_as_float(r[o + 1]),
-                          __uint_as_float(r[o + 2]), __uint_as_float(r[o + 3]));
-          }
-        }
-      }
-      if (warp == 4 && lane == 0) f_trace(a, t, 3);
-    };
-    int td = 0, ts = 0;
-    uint32_t idle = 0;
-#pragma unroll 1
-    while (ts < ntiles) {
-      int act = 0;
-      if (lane == 0) {
-        if (ts < td && u_mbar_test(&sm.rfull[ts & 1], (uint32_t)((ts >> 1) & 1))) act = 1;
-        // a slot is refilled only after this warp's own sum of its previous tile (td - ts < 2) and after every owner
-        // has released it (rfree); both are probed here so that a pending sum is never stuck behind a blocked drain
-        else if (td < ntiles && td - ts < 2 && u_mbar_test(&sm.sfull[td & 1], (uint32_t)((td >> 1) & 1)) &&
-                 (td < 2 || u_mbar_test(&sm.rfree[td & 1], (uint32_t)(((td >> 1) + 1) & 1)))) act = 2;
-        if (!act) {   // sleep in hardware on the more likely event
-          if (ts < td) u_mbar_try(&sm.rfull[ts & 1], (uint32_t)((ts >> 1) & 1), 150);
-          else if (td < ntiles) u_mbar_try(&sm.sfull[td & 1], (uint32_t)((td >> 1) & 1), 150);
-        }
-      }
-      act = __shfl_sync(0xffffffffu, act, 0);
-      if (act == 1) { l1sum(ts); ++ts; idle = 0; }
-      else if (act == 2) { drain(td); ++td; idle = 0; }
-      else if (++idle > kFSpinLimit) f_timeout(a, 0x330, (uint32_t)td, (uint32_t)ts);
     }
   } else if (warp >= 8 && warp < 12) {
     // ============================================================ weights -> tensor memory, z, final epilogue
@@ -515,8 +551,8 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t seq = epoch0 + (uint32_t)t;
       const int ring = (int)(seq % kFRing);
-      const uint32_t tag4 = seq & 15u;
-      // published weights: [ring][job 32][q 64][4 rows] fp32 whose low 4 mantissa bits carry the tile's sequence number:
+      const uint32_t tag4 = (seq / kFRing) & 15u;    // the slot's previous occupant carries tag4 - 1
+      // published weights: [ring][job 32][q 64][4 rows] fp32 whose low 4 mantissa bits carry the tile's round (seq / ring):
       // every word validates itself, so the jobs need no fence and no flag and the consumers no acquire -- the slot's
       // previous occupant is exactly kFRing tiles older (ring slot = seq mod kFRing, gap-free over launches).
       const uint32_t* wr = reinterpret_cast<const uint32_t*>(a.ar.gw) + (size_t)ring * (32 * 64 * 4);
@@ -535,6 +571,10 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
             seen = __shfl_sync(0xffffffffu, seen, 0);
             if (!seen && ++spin > kFSpinLimit) f_timeout(a, 0x400, (uint32_t)t, tag4);
           } while (!seen);
+          if (warp == 8 && lane == 0) {     // the weights are on their way: start the second read of the tile (L2)
+            if (t >= C::kSB) f_wait(a, &sm.bempty[t % C::kSB], (uint32_t)(((t / C::kSB) + 1) & 1), 0x121, t);
+            load_tile(sm.stages + (size_t)(C::kSA + t % C::kSB) * kFStageBytes, &sm.bfull[t % C::kSB], t, pol_drop);
+          }
         }
         uint4 wv[8];
         {
@@ -576,7 +616,7 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
           pk[16 + j] = part ? f_pack_bf16(k0 - h0, k1 - h1) : f_pack_bf16(h0, h1);
         }
         if (t >= 2) { f_wait(a, &sm.pempty[b], (uint32_t)(((t >> 1) + 1) & 1), 0x410, t); u_fence_after(); }
-        u_tmem_st32(tlane + kFColP + (uint32_t)b * 64, pk);
+        u_tmem_st32(tlane + C::kColP + (uint32_t)b * C::kPStride, pk);
       } else {
         uint32_t ph[32], pl[32];
         const uint32_t* wq = wr + ((size_t)(q >> 6) * kFJobsPerGroup * 64 + (q & 63)) * 4;
@@ -592,6 +632,10 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
             seen = __shfl_sync(0xffffffffu, seen, 0);
             if (!seen && ++spin > kFSpinLimit) f_timeout(a, 0x400, (uint32_t)t, tag4);
           } while (!seen);
+          if (warp == 8 && lane == 0) {     // the weights are on their way: start the second read of the tile (L2)
+            if (t >= C::kSB) f_wait(a, &sm.bempty[t % C::kSB], (uint32_t)(((t / C::kSB) + 1) & 1), 0x121, t);
+            load_tile(sm.stages + (size_t)(C::kSA + t % C::kSB) * kFStageBytes, &sm.bfull[t % C::kSB], t, pol_drop);
+          }
         }
 #pragma unroll
         for (int hv = 0; hv < 2; ++hv) {          // rows [32 hv, 32 hv + 32): 8 lines of 4 rows
@@ -620,8 +664,8 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
         }
         if (warp == 8 && lane == 0) f_trace(a, t, 6);
         if (t >= 2) { f_wait(a, &sm.pempty[b], (uint32_t)(((t >> 1) + 1) & 1), 0x410, t); u_fence_after(); }
-        u_tmem_st32(tlane + kFColP + (uint32_t)b * 64, ph);
-        u_tmem_st32(tlane + kFColP + (uint32_t)b * 64 + 32, pl);
+        u_tmem_st32(tlane + C::kColP + (uint32_t)b * C::kPStride, ph);
+        u_tmem_st32(tlane + C::kColP + (uint32_t)b * C::kPStride + 32, pl);
       }
       u_tmem_st_wait();
       u_fence_before();
@@ -638,7 +682,7 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
 #pragma unroll 1
       for (int c = 0; c < kFDS / 32; ++c) {
         uint32_t r[32];
-        u_tmem_ld32_nowait(tlane + kFColAcc + c * 32, r);
+        u_tmem_ld32_nowait(tlane + C::kColAcc + c * 32, r);
         u_tmem_ld_wait();
         if constexpr (G == 1) {
           float v[16];
@@ -738,18 +782,20 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    // ---- jobs (tile t, query group g, rows [4j, 4j+4)) dealt round-robin over all CTAs.  Thread = (query row,
-    //      row pair): lane l of warp w reads line 32 w + l of the job's 2 KiB block of every cluster (512 contiguous
-    //      bytes per warp instruction) and sums the clusters in order.
+    // ---- level-2 work units (tile t, query group g, rows [4j, 4j+4), half h of the group's 64 query rows) dealt
+    //      round-robin over all 4 x #CTAs warps of this role: every warp is an independent worker (a worker blocks on
+    //      its unit until the slowest cluster has delivered, so the tiles between two units of one worker bound the
+    //      rate: 16 G tiles here).  Lane l reads lines l and 32 + l of the unit's 1 KiB block of every cluster (512
+    //      contiguous bytes per warp instruction) = (query row, row pair) twice, and sums the clusters in order.
     {
-      const int q64 = ow * 16 + (lane >> 1);
       const int lh = lane & 1;
-      const int njobs = ntiles * C::kJobs;
+      const int nunits = ntiles * C::kJobs * 2;
+      const int nworkers = nctas * 4;
 #pragma unroll 1
-      for (int J = cta; J < njobs; J += nctas) {
-        const int t = J / C::kJobs, jj = J - t * C::kJobs;
+      for (int U = cta * 4 + ow; U < nunits; U += nworkers) {
+        const int t = U / (C::kJobs * 2), rem = U - t * (C::kJobs * 2);
+        const int jj = rem >> 1, qh = rem & 1;
         const int j = jj & (kFJobsPerGroup - 1), g = jj / kFJobsPerGroup;
-        const int q = g * 64 + q64;
         const uint32_t tag = epoch0 + (uint32_t)t;
         const int ring = (int)(tag % kFRing);
         const int row = t * kFR + j * kFJobRows + lh * 2;
@@ -757,9 +803,10 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
         const float sq0 = row < a.N ? __ldg(a.sqnorm + row) : 0.f;
         const float sq1 = row + 1 < a.N ? __ldg(a.sqnorm + row + 1) : 0.f;
         const size_t cl_stride = (size_t)32 * 2048;
-        const uint8_t* src0 = a.ar.part_ll + (size_t)ring * kFMaxClusters * cl_stride + (size_t)jj * 2048 + (size_t)tid * 16;
-        // A job usually arrives long before its tile: ONE lane per warp probes one line, with back-off, until the tile
-        // shows up (every owner warp of every CTA spinning on full-width loads saturates the L1s and L2)
+        const uint8_t* src0 = a.ar.part_ll + (size_t)ring * kFMaxClusters * cl_stride + (size_t)jj * 2048 +
+                              (size_t)(qh * 64 + lane) * 16;
+        // A unit usually arrives long before its tile: ONE lane probes one line, with back-off, until the tile shows up
+        // (every worker spinning on full-width loads saturates the L1s and L2)
         {
           uint32_t spin = 0;
           int seen = 0;
@@ -767,49 +814,58 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
             if (lane == 0) {
               const uint4 l0 = u_ll_load(src0);
               seen = (l0.y == tag && l0.w == tag) ? 1 : 0;
-              if (!seen) __nanosleep(20);
+              if (!seen) __nanosleep(a.poll_sleep);
             }
             seen = __shfl_sync(0xffffffffu, seen, 0);
-            if (!seen && ++spin > kFSpinLimit) f_timeout(a, 0x508, (uint32_t)t, (uint32_t)jj);
+            if (!seen && ++spin > kFSpinLimit) f_timeout(a, 0x508, (uint32_t)t, (uint32_t)rem);
           } while (!seen);
           if (ow == 0 && lane == 0) f_trace(a, t, 9);
         }
-        float dv0 = 0.f, dv1 = 0.f;
-        for (int k0 = 0; k0 < nclusters; k0 += 16) {
-          uint4 ln[16];
+        float da0 = 0.f, da1 = 0.f, db0 = 0.f, db1 = 0.f;      // lines l (a) and 32 + l (b), rows lh*2 and lh*2+1
+        for (int k0 = 0; k0 < nclusters; k0 += 8) {
+          uint4 la[8], lb[8];
           uint32_t spin = 0;
           bool ok;
           do {
             ok = true;
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < 8; ++u) {
               const int k = min(k0 + u, nclusters - 1);
-              ln[u] = u_ll_load(src0 + (size_t)k * cl_stride);
-              ok = ok && ln[u].y == tag && ln[u].w == tag;
+              la[u] = u_ll_load(src0 + (size_t)k * cl_stride);
+              lb[u] = u_ll_load(src0 + (size_t)k * cl_stride + 512);
+              ok = ok && la[u].y == tag && la[u].w == tag && lb[u].y == tag && lb[u].w == tag;
             }
-            if (!ok && ++spin > kFSpinLimit) f_timeout(a, 0x510, (uint32_t)t, (uint32_t)(jj * 256 + k0));
+            if (!ok && ++spin > kFSpinLimit) f_timeout(a, 0x510, (uint32_t)t, (uint32_t)(rem * 256 + k0));
           } while (!ok);
 #pragma unroll
-          for (int u = 0; u < 16; ++u)
-            if (k0 + u < nclusters) { dv0 += __uint_as_float(ln[u].x); dv1 += __uint_as_float(ln[u].z); }
+          for (int u = 0; u < 8; ++u)
+            if (k0 + u < nclusters) {
+              da0 += __uint_as_float(la[u].x); da1 += __uint_as_float(la[u].z);
+              db0 += __uint_as_float(lb[u].x); db1 += __uint_as_float(lb[u].z);
+            }
         }
         if (ow == 0 && lane == 0) f_trace(a, t, 10);
-        const float xs = sm.xsq[q];
-        float k0v = 0.f, k1v = 0.f;
-        if (q < a.Q) {
-          if (row < a.N) k0v = expf(-dist_from_dot(xs, sq0, dv0, a.alpha, a.power) * a.inv2s2);
-          if (row + 1 < a.N) k1v = expf(-dist_from_dot(xs, sq1, dv1, a.alpha, a.power) * a.inv2s2);
-        }
-        // the weights carry the low 4 bits of the sequence number in their low mantissa bits (2^-19 relative): no fence,
-        // no flag -- each 32-bit word is valid on its own
-        {
-          const uint32_t b0 = (__float_as_uint(k0v) & ~15u) | (tag & 15u), b1 = (__float_as_uint(k1v) & ~15u) | (tag & 15u);
+        const uint32_t tagbits = (tag / kFRing) & 15u;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int q64 = qh * 32 + i * 16 + (lane >> 1);
+          const int q = g * 64 + q64;
+          const float d0v = i ? db0 : da0, d1v = i ? db1 : da1;
+          const float xs = sm.xsq[q];
+          float k0v = 0.f, k1v = 0.f;
+          if (q < a.Q) {
+            if (row < a.N) k0v = expf(-dist_from_dot(xs, sq0, d0v, a.alpha, a.power) * a.inv2s2);
+            if (row + 1 < a.N) k1v = expf(-dist_from_dot(xs, sq1, d1v, a.alpha, a.power) * a.inv2s2);
+          }
+          // the weights carry the tile's round (seq / ring) in their low 4 mantissa bits (2^-19 relative): no fence, no
+          // flag -- each 32-bit word is valid on its own
+          const uint32_t b0 = (__float_as_uint(k0v) & ~15u) | tagbits, b1 = (__float_as_uint(k1v) & ~15u) | tagbits;
           asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};"
                        ::"l"(a.ar.gw + (((size_t)ring * 32 + jj) * 64 + q64) * 4 + lh * 2), "r"(b0), "r"(b1) : "memory");
-        }
-        if (a.k_out && q < a.Q) {
-          if (row < a.N) a.k_out[(int64_t)q * a.N + row] = k0v;
-          if (row + 1 < a.N) a.k_out[(int64_t)q * a.N + row + 1] = k1v;
+          if (a.k_out && q < a.Q) {
+            if (row < a.N) a.k_out[(int64_t)q * a.N + row] = k0v;
+            if (row + 1 < a.N) a.k_out[(int64_t)q * a.N + row + 1] = k1v;
+          }
         }
         if (ow == 0 && lane == 0) f_trace(a, t, 11);
       }
@@ -865,8 +921,8 @@ int arena_get(int dev, ArenaHost** out) {
     h.ar.gw = reinterpret_cast<float*>(p); p += kGwBytes;
     p += 256;
     h.ar.wflag = reinterpret_cast<uint32_t*>(p);
-    const uint32_t one[2] = {1, 1};
-    SDN_CUDA_OK(cudaMemcpy(h.ar.epoch, one, sizeof(one), cudaMemcpyHostToDevice));   // tags start at 1: zeroed lines never match
+    const uint32_t one[2] = {kFRing, 1};     // sequence numbers start in round 1: the zeroed rings (round-tag 0, LL tag 0) never match
+    SDN_CUDA_OK(cudaMemcpy(h.ar.epoch, one, sizeof(one), cudaMemcpyHostToDevice));
     void* dh = nullptr;
     if (cudaHostAlloc(&dh, 64, cudaHostAllocMapped) == cudaSuccess) {
       memset(dh, 0, 64);
@@ -999,7 +1055,11 @@ int flash_run(const void* planes, const float* sqnorm, int64_t N, int64_t D, con
     if (h->max_clusters[G] < nclusters) return SDN_E_UNSUPPORTED;    // the grid must be co-resident
     FlashArgs a{};
     a.xq = xq + q0 * D; a.sqnorm = sqnorm; a.Q = qn; a.N = (int)N; a.ntiles = (int)cdiv(N, kFR); a.nclusters = nclusters;
-    a.D = D; a.inv2s2 = inv2s2; a.alpha = alpha; a.power = power;
+    static const int window = [] { const char* e = getenv("SDN_FLASH_WINDOW"); const int v = e ? atoi(e) : 0; return v >= 1 && v < kFRing ? v : kFWindow; }();
+    static const int mma_sleep = [] { const char* e = getenv("SDN_FLASH_MMA_SLEEP"); return e ? atoi(e) : 40; }();
+    static const int poll_sleep = [] { const char* e = getenv("SDN_FLASH_POLL_SLEEP"); return e ? atoi(e) : 100; }();
+    a.mma_sleep = (unsigned)mma_sleep; a.poll_sleep = (unsigned)poll_sleep;
+    a.window = window; a.D = D; a.inv2s2 = inv2s2; a.alpha = alpha; a.power = power;
     a.num_out = num_out ? num_out + q0 * D : nullptr;
     a.z_out = z_out ? z_out + q0 : nullptr;
     a.k_out = k_out ? k_out + q0 * N : nullptr;

@@ -36,14 +36,13 @@ def main(Q=64, N=3000):
         if v.size:
             print(f"{name}: mean {v.mean():.0f}  p50 {np.median(v):.0f}  max {v.max():.0f}  n={v.size}")
     tr = raw.copy()
-    tr[:, :, 12:] = 0
     ntiles = min(64, (N + 63) // 64)
     t0 = tr[:, :ntiles, 0][tr[:, :ntiles, 0] > 0].min()
     tr = np.where(tr > 0, tr - t0, np.nan)
     print(f"Q={Q} N={N}: {ntiles} tiles traced; all times in us relative to the first TMA issue")
-    for cta in (0, 37, 127):
+    for cta in (0, 1, 2, 3, 127):
         print(f"-- CTA {cta}: per tile  " + " | ".join(EV[:9]))
-        for t in list(range(0, min(ntiles, 14))) + list(range(max(14, ntiles - 3), ntiles)):
+        for t in list(range(0, min(ntiles, 6))) + list(range(20, min(ntiles, 30))) + list(range(max(30, ntiles - 2), ntiles)):
             print(f"   t={t:3d} " + " ".join(f"{tr[cta, t, e] / 1e3:8.2f}" for e in range(9)))
     # owner events live on the owner CTA: take the min / max over CTAs per tile
     print("-- per tile over all CTAs (us): tma(min) A(max) sent(max) l1stored(max) | job seen(min..max) loaded(max) flag(max) | w seen(min..max) P(max) B(min..max)")
@@ -52,6 +51,18 @@ def main(Q=64, N=3000):
         print(f"   t={t:3d} {g(0, np.nanmin):7.2f} {g(1, np.nanmax):7.2f} {g(3, np.nanmax):7.2f} {g(5, np.nanmax):7.2f} | "
               f"{g(9, np.nanmin):7.2f}..{g(9, np.nanmax):7.2f} {g(10, np.nanmax):7.2f} {g(11, np.nanmax):7.2f} | "
               f"{g(6, np.nanmin):7.2f}..{g(6, np.nanmax):7.2f} {g(7, np.nanmax):7.2f} {g(8, np.nanmin):7.2f}..{g(8, np.nanmax):7.2f}")
+    print("-- CTA 0 drain loop: top | rfree ok | sfull ok | staged+bar | bulk issued   (us)")
+    for t in range(20, min(ntiles, 30)):
+        print(f"   t={t:3d} " + " ".join(f"{tr[0, t, e] / 1e3:8.2f}" for e in (12, 13, 2, 14, 3)))
+    lo, hi = min(10, ntiles - 2), ntiles - 1
+    for e, name in ((1, "A issue"), (3, "bulk sent"), (5, "l1 stored"), (6, "w seen"), (8, "B issue")):
+        per = (tr[:, hi, e] - tr[:, lo, e]) / (hi - lo) / 1e3
+        print(f"period of {name:10s} over tiles {lo}..{hi}: mean {np.nanmean(per):.2f} us  min {np.nanmin(per):.2f}  max {np.nanmax(per):.2f}")
+    wait_rfree = (tr[:, lo:hi, 13] - tr[:, lo:hi, 12]) / 1e3
+    body = (tr[:, lo:hi, 3] - tr[:, lo:hi, 13]) / 1e3
+    print(f"drain loop: rfree wait mean {np.nanmean(wait_rfree):.2f} us (per-CTA max of means {np.nanmax(np.nanmean(wait_rfree, axis=1)):.2f}), body mean {np.nanmean(body):.2f} us")
+    lag_cl = np.nanmax(tr[:, lo:hi, 5], axis=0) - np.nanmin(tr[:, lo:hi, 5], axis=0)
+    print(f"skew of 'l1 stored' over the CTAs, per tile: mean {np.nanmean(lag_cl) / 1e3:.2f} us")
     d = lambda a_, b_: np.nanmean(tr[:, 2:ntiles, b_] - tr[:, 2:ntiles, a_]) / 1e3
     print(f"mean per-CTA deltas (us): tma->A {d(0,1):.2f}  A->drain {d(1,2):.2f}  drain->sent {d(2,3):.2f}  sent->l1 {d(3,4):.2f}  "
           f"l1->stored {d(4,5):.2f}  stored->w seen {d(5,6):.2f}  w seen->P {d(6,7):.2f}  P->B {d(7,8):.2f}  tma->B {d(0,8):.2f}")
