@@ -16,7 +16,7 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - no hidden allocation: scratch is caller-provided, its size comes from
  *     the matching *_workspace_bytes() call.  Two exceptions: the *_host convenience
- *     calls own a cached device staging area, and SDN_PATH_FLASH owns ~9 MB of
+ *     calls own a cached device staging area, and SDN_PATH_FLASH owns ~37 MB of
  *     per-device synchronisation memory (exchange rings of its persistent grid,
  *     allocated and zeroed at its first call on a device -- so make that first call
  *     outside a CUDA-graph capture; calls of that path on one device must be stream-ordered
@@ -57,10 +57,12 @@ enum {
   SDN_PATH_UMMA = 3,      /* tcgen05 / TMEM / TMA two-phase kernels, batched Q */
   SDN_PATH_UMMA_BF16 = 4, /* same kernels reading ONLY the bf16 hi plane of the bank: half the bytes per pass,
                              outside the 1e-3 parity tolerance near a negative; explicit opt-in, never AUTO */
-  SDN_PATH_FLASH = 5      /* ONE-pass tcgen05 kernel, batched Q: every bank tile stays in shared memory between the
-                             distance contraction and the weighted accumulation (persistent grid of D/128 CTAs,
-                             cross-CTA reduction over DSMEM + L2).  D % 1024 == 0, 8192 <= D <= 16384 (SD-1.4 latents);
-                             AUTO prefers it over SDN_PATH_UMMA whenever the shape fits */
+  SDN_PATH_FLASH = 5      /* ONE-HBM-pass tcgen05 kernel, batched Q: both contractions in one persistent grid of D/128
+                             co-resident CTAs, a few tiles apart, so that the second read of a bank tile hits the L2;
+                             the dot products are reduced across the CTAs through L2 inside the kernel.
+                             D % 1024 == 0, 8192 <= D <= 16384 (SD-1.4 latents), 64 query rows per pass.  Explicit opt-in
+                             (or SDN_PREFER_FLASH=1 in the environment): it reads the bank once but is not yet faster
+                             than SDN_PATH_UMMA */
 };
 
 /* Epilogue flags (bit-or). */
@@ -204,14 +206,14 @@ int sdn_epilogue_flow(const float* num, const float* z, int64_t Q, int64_t D,
  * no channel normalisation (fast.py:120-132, threshold.py:171-193).
  *   Q <= 8 : the one-pass kernel computes ||x||^2 itself and the per-cluster reduction applies the correction
  *            (2 launches);
- *   Q > 8  : SDN_PATH_FLASH shapes: ONE launch (query planes, ||x||^2, both contractions, the cross-CTA reduction
- *            and the correction in the same persistent kernel; the bank is read once); otherwise
- *            (needs `planes` and z_out) query planes + ||x||^2 in one kernel, correction fused into the epilogue
+ *   Q > 8  : (needs `planes` and z_out) query planes + ||x||^2 in one kernel, correction fused into the epilogue
  *            of phase B (5 launches instead of 8).  One pass over the bank serves up to 128 query rows (two groups
  *            of 64 sharing every bank tile; the small element-wise kernels run once per group), more rows take
  *            ceil(Q / 128) passes.
  * x0_inout [Q,D] is corrected in place; num_out / neg_out / k_out are optional extra outputs; mean_out is zeroed
- * by the call.  `path`: SDN_PATH_AUTO, or SDN_PATH_STREAM / SDN_PATH_UMMA / SDN_PATH_FLASH to force one family.
+ * by the call.  `path`: SDN_PATH_AUTO, or SDN_PATH_STREAM / SDN_PATH_UMMA / SDN_PATH_FLASH to force one family
+ * (SDN_PATH_FLASH: ONE launch -- query planes, ||x||^2, both contractions, the cross-CTA reduction and the correction
+ * in the same persistent kernel; the bank is read from HBM once).
  * Returns SDN_E_UNSUPPORTED for shapes the selected fused path does not take (callers then use the three-call
  * sequence).  Workspace: sdn_repel_workspace_bytes(Q, N, D, SDN_PATH_AUTO). */
 int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* planes, int64_t N, int64_t D,

@@ -1,5 +1,6 @@
 // extern "C" entry points: argument checking, kernel-family dispatch, host-buffer convenience.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -19,7 +20,10 @@ static bool batched(int64_t Q, int64_t N) { return Q > 8 || (Q > 4 && N >= 1024)
 
 static int pick_path(int32_t path, int64_t Q, int64_t N, int64_t D, const void* planes) {
   if (path == SDN_PATH_AUTO) {
-    if (flash_supported(Q, N, D, planes) && batched(Q, N)) return SDN_PATH_FLASH;
+    // SDN_PATH_FLASH (one HBM pass) is opt-in: measured on B200 it is still slower than the two-phase kernels (its
+    // weights exchange costs ~2 us per 64-row tile), except with SDN_PREFER_FLASH=1
+    static const bool prefer_flash = [] { const char* e = getenv("SDN_PREFER_FLASH"); return e && atoi(e) != 0; }();
+    if (prefer_flash && flash_supported(Q, N, D, planes) && batched(Q, N)) return SDN_PATH_FLASH;
     if (umma_supported(Q, N, D, planes) && batched(Q, N)) return SDN_PATH_UMMA;
     if (stream_supported(Q, N, D)) return SDN_PATH_STREAM;
     return SDN_PATH_GENERIC;
@@ -172,7 +176,7 @@ int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* p
   cudaStream_t st = (cudaStream_t)stream;
   const bool want_batched = path == SDN_PATH_AUTO ? batched(Q, N) : path != SDN_PATH_STREAM;
   if (path == SDN_PATH_FLASH && !flash_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
-  if (want_batched && (path == SDN_PATH_AUTO || path == SDN_PATH_FLASH) && flash_supported(Q, N, D, planes)) {
+  if (want_batched && pick_path(path, Q, N, D, planes) == SDN_PATH_FLASH) {
     FlashEpi e{};
     e.fused = 1; e.eps = eps; e.scale = scale; e.gate_thr = gate_threshold; e.flags = flags;
     e.x0 = x0_inout; e.neg_out = neg_out; e.denom_out = denom_out; e.gate_out = gate_out; e.mean_out = mean_out;

@@ -219,11 +219,10 @@ def test_new_entry_points_validate_arguments(nv):
     assert L.sdn_set_option(nv.OPT_SKIP_NEGLIGIBLE, 1) == 0
     assert L.sdn_set_option(12345, 1) == -4
     assert L.sdn_repel_path(1, 515, 16384, 0, nv.PATH_AUTO) == nv.PATH_STREAM
-    assert L.sdn_repel_path(64, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_FLASH       # one pass over the bank
-    assert L.sdn_repel_path(128, 30000, 16384, 1, nv.PATH_AUTO) == nv.PATH_FLASH
-    assert L.sdn_repel_path(16, 515, 65536, 1, nv.PATH_AUTO) == nv.PATH_UMMA         # SD3: more d-blocks than SMs
-    assert L.sdn_repel_path(16, 515, 4096, 1, nv.PATH_AUTO) == nv.PATH_UMMA          # too few d-blocks to fill the GPU
-    assert L.sdn_repel_path(8, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_FLASH        # FMA-bound for the cluster kernel
+    assert L.sdn_repel_path(64, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_UMMA        # the one-pass kernel is opt-in
+    assert L.sdn_repel_path(64, 3000, 16384, 1, nv.PATH_FLASH) == nv.PATH_FLASH
+    assert L.sdn_repel_path(16, 515, 65536, 1, nv.PATH_AUTO) == nv.PATH_UMMA
+    assert L.sdn_repel_path(8, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_UMMA         # FMA-bound for the cluster kernel
     assert L.sdn_repel_path(8, 515, 16384, 1, nv.PATH_AUTO) == nv.PATH_STREAM
     assert L.sdn_repel_path(4, 3000, 16384, 1, nv.PATH_AUTO) == nv.PATH_STREAM
     assert L.sdn_repel_path(64, 3000, 16384, 0, nv.PATH_AUTO) == nv.PATH_GENERIC     # no planes: CUDA cores

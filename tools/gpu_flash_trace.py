@@ -51,16 +51,13 @@ def main(Q=64, N=3000):
         print(f"   t={t:3d} {g(0, np.nanmin):7.2f} {g(1, np.nanmax):7.2f} {g(3, np.nanmax):7.2f} {g(5, np.nanmax):7.2f} | "
               f"{g(9, np.nanmin):7.2f}..{g(9, np.nanmax):7.2f} {g(10, np.nanmax):7.2f} {g(11, np.nanmax):7.2f} | "
               f"{g(6, np.nanmin):7.2f}..{g(6, np.nanmax):7.2f} {g(7, np.nanmax):7.2f} {g(8, np.nanmin):7.2f}..{g(8, np.nanmax):7.2f}")
-    print("-- CTA 0 drain loop: top | rfree ok | sfull ok | staged+bar | bulk issued   (us)")
+    print("-- CTA 0 weights loop: top | loads ok | converted | pempty ok | P stored | B issued   (us)")
     for t in range(20, min(ntiles, 30)):
-        print(f"   t={t:3d} " + " ".join(f"{tr[0, t, e] / 1e3:8.2f}" for e in (12, 13, 2, 14, 3)))
+        print(f"   t={t:3d} " + " ".join(f"{tr[0, t, e] / 1e3:8.2f}" for e in (12, 6, 13, 14, 7, 8)))
     lo, hi = min(10, ntiles - 2), ntiles - 1
     for e, name in ((1, "A issue"), (3, "bulk sent"), (5, "l1 stored"), (6, "w seen"), (8, "B issue")):
         per = (tr[:, hi, e] - tr[:, lo, e]) / (hi - lo) / 1e3
         print(f"period of {name:10s} over tiles {lo}..{hi}: mean {np.nanmean(per):.2f} us  min {np.nanmin(per):.2f}  max {np.nanmax(per):.2f}")
-    wait_rfree = (tr[:, lo:hi, 13] - tr[:, lo:hi, 12]) / 1e3
-    body = (tr[:, lo:hi, 3] - tr[:, lo:hi, 13]) / 1e3
-    print(f"drain loop: rfree wait mean {np.nanmean(wait_rfree):.2f} us (per-CTA max of means {np.nanmax(np.nanmean(wait_rfree, axis=1)):.2f}), body mean {np.nanmean(body):.2f} us")
     lag_cl = np.nanmax(tr[:, lo:hi, 5], axis=0) - np.nanmin(tr[:, lo:hi, 5], axis=0)
     print(f"skew of 'l1 stored' over the CTAs, per tile: mean {np.nanmean(lag_cl) / 1e3:.2f} us")
     d = lambda a_, b_: np.nanmean(tr[:, 2:ntiles, b_] - tr[:, 2:ntiles, a_]) / 1e3
