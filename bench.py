@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--path", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 stream, 3 tcgen05, 4 tcgen05 reading only the bf16 hi plane")
+    ap.add_argument("--path", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 stream, 3 two-phase tcgen05, 4 tcgen05 reading only the bf16 hi plane, "
+                         "5 one-pass tcgen05 (one HBM read of the bank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling: the bank grows with the GPU count (N x gpus rows, a fixed N-row shard per GPU) -- "
@@ -112,30 +113,60 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------------- CPU baseline
 def cpu_reference_arm(wl, steps, warmup, sample_q=4):
-    """The reference's CPU path: oracle.materialised_port (same op chain as fast.py:249-257) on all
-    host threads.  One step = conditioning of `sample_q` query rows against the full bank."""
+    """The reference's CPU path on all host threads.  `kind` "reference": the UNMODIFIED reference module
+    (oracle/_ref, made by oracle/build_ref.py where /root/reference exists) -- kernel_fast.conditioning(); `kind`
+    "port": oracle.materialised_port (the same op chain as fast.py:249-257) when the copy is absent.
+    One step = conditioning of `sample_q` query rows against the full bank (the reference's [Q,N,D+1] temporaries
+    do not fit at Q = 64)."""
+    import tempfile
     import torch
     from oracle import repellency_oracle as orc
+    from oracle import build_ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     bank = orc.synthetic_bank(wl["N"], wl["C"], wl["H"], wl["W"])
     q = min(sample_q, wl["Q"])
+    if wl["kind"] == "threshold":
+        q = 1                      # the reference threshold module takes one query row (SURVEY Q6)
     x = orc.synthetic_queries(bank, q, "near")
     sdv3 = wl["kind"] == "fast_sdv3"
     sigma = wl["sigma"]
-    for _ in range(max(warmup, 1)):
-        orc.conditioning_port(x.clone(), bank, wl["scale"], sigma, 1e-8, sdv3)
+    kind, call = "port", None
+    try:
+        mod = build_ref.load({"fast": "fast", "fast_sdv3": "fast_sdv3", "threshold": "threshold"}[wl["kind"]])
+    except Exception:
+        mod = None
+    if mod is not None:
+        path = os.path.join(tempfile.mkdtemp(prefix="sdn_bench_ref_"), "proj_ref.pt")
+        torch.save(bank.clone(), path)
+        kw = dict(n_embed=16, proj_ref_path=path, cache_proj_ref=True, scale=wl["scale"])
+        if wl["kind"] == "threshold":
+            kw.update(sigma=sigma, beta_threshold=1.0, beta_threshold_margin=0.0)
+        with torch.no_grad():
+            obj = mod.get_repellency_method("kernel_fast", ref_data=torch.zeros(1, 3, 8, 8), embed_fn=None, forward_fn=None,
+                                            num_timesteps=50, max_idx=1000, beta_min=0.00085, beta_max=0.012, **kw)
+        kind = "reference"
+        if wl["kind"] == "threshold":
+            call = lambda xin: obj.conditioning(xin, beta_threshold=True)      # noqa: E731
+        else:
+            call = lambda xin: obj.conditioning(xin)                           # noqa: E731
+    else:
+        call = lambda xin: orc.conditioning_port(xin, bank, wl["scale"], sigma, 1e-8, sdv3)   # noqa: E731
     times = []
-    for _ in range(steps):
-        xin = x.clone()
-        t0 = time.perf_counter()
-        orc.conditioning_port(xin, bank, wl["scale"], sigma, 1e-8, sdv3)
-        times.append(time.perf_counter() - t0)
+    with torch.no_grad():
+        for _ in range(max(warmup, 1)):
+            call(x.clone())
+        for _ in range(steps):
+            xin = x.clone()
+            t0 = time.perf_counter()
+            call(xin)
+            times.append(time.perf_counter() - t0)
     total = sum(times)
+    what = ("the reference module itself (oracle/_ref: repellency_methods_%s.kernel_fast.conditioning, fp32 torch on CPU)" % wl["kind"]
+            if kind == "reference" else "float32 torch op chain of the reference (oracle.materialised_port)")
     return {"value": q * steps / total, "unit": "projections/s", "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": f"{steps} calls x {q} query rows (of Q={wl['Q']}) against the full N={wl['N']} bank, "
-                      f"float32 torch op chain of the reference (oracle.materialised_port); "
+            "kind": kind,
+            "sample": f"{steps} calls x {q} query rows (of Q={wl['Q']}) against the full N={wl['N']} bank, {what}; "
                       f"best call {min(times)*1e3:.1f} ms",
             "ms_per_step": 1e3 * total / steps, "q": q}
 
@@ -197,8 +228,9 @@ def main():
                      "e2e": {"value": r["value"], "unit": "projections/s", "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": 0},
                      "gpu_launches": 0})
-        line["config"] = dict(base["config"], note="reference arm: the reference is pure Python with no "
-                              "package to install; its CPU op chain is timed via the oracle port on the host cores")
+        line["config"] = dict(base["config"], note="reference arm: the reference is a flat pure-Python repo (nothing to pip "
+                              "install); its own module is timed on the host cores from oracle/_ref when present (kind "
+                              "'reference'), else the oracle's op-chain port (kind 'port')")
         emit(line)
         return
 
@@ -259,11 +291,11 @@ def main():
     # ---- timed region: K steps, each between its own CUDA events, L2 flushed in between ----
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    gate = 1.0 if wl["kind"] == "threshold" else None
     # kernels per step: counted on one eager call (graph replays launch the same kernel nodes)
     x.copy_(x_src)
     c0 = nv.launch_count()
-    proj.correct(x, sigma, scale, eps, normalize_channels=normalize,
-                 gate_threshold=(1.0 if wl["kind"] == "threshold" else None))
+    proj.correct(x, sigma, scale, eps, normalize_channels=normalize, gate_threshold=gate)
     launches_per_step = nv.launch_count() - c0
     barrier()
     for i in range(args.steps):
@@ -274,70 +306,81 @@ def main():
         ev1[i].record()
     barrier()
     launches = launches_per_step * args.steps
-    total_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    # a step of the job ends when its slowest rank ends: per-step max over ranks, then the sum
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in zip(ev0, ev1)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+    step_sorted = sorted(step_ms.tolist())
+    total_ms = float(step_ms.sum().item())
     ms_per_step = total_ms / args.steps
     value = Q * args.steps / (total_ms * 1e-3)
+    pct = lambda f: step_sorted[min(len(step_sorted) - 1, int(f * len(step_sorted)))]   # noqa: E731
 
-    # ---- roofline: the bank-streaming stage (sdn_repel_partial) between CUDA events on its stream, and each
-    # ---- kernel inside it between the library's own events (sdn_profile_*), L2 flushed before every call
-    s = proj._get(Q, normalize > 0)
-    p0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    p1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # ---- parity of the timed path, in the same run: the corrected queries of one more step against the float64
+    # ---- oracle on two query rows (N = 1), and against rank 0's own full-bank single-GPU projection (N > 1)
     x.copy_(x_src)
-    if args.path in (0, 3, 4) and (Q > 8 or (Q > 4 and bank.N >= 1024)) and D % 128 == 0:
-        bank.ensure_planes()
+    step()
+    torch.cuda.synchronize()
+    got = x.detach().reshape(Q, D).clone()
+    parity = None
+    rows = [0, Q - 1] if Q > 1 else [0]
+    if rank == 0:
+        import numpy as np
+        want = orc.conditioning_fast(x_src[rows].cpu().numpy(), bank_cpu.numpy(), scale=scale, sigma=sigma,
+                                     sdv3=(wl["kind"] == "fast_sdv3"))["x_0_hat"].reshape(len(rows), D)
+        g = got[rows].cpu().numpy().astype(np.float64)
+        moved = float(np.abs(want - x_src[rows].reshape(len(rows), D).cpu().numpy()).max())
+        parity = {"vs": "float64 oracle (oracle.closed_form) on query rows %s, full bank" % rows,
+                  "max_rel_err_x0": float(np.abs(g - want).max() / np.abs(want).max()),
+                  "correction_linf": moved, "tolerance": 1e-3}
+        if world > 1:
+            full = NegativeBank(bank_cpu.to(dev), with_planes=True)
+            xs = x_src.clone()
+            Projector(full, path=args.path).correct(xs, sigma, scale, eps, normalize_channels=normalize, gate_threshold=gate)
+            torch.cuda.synchronize()
+            ref1 = xs.reshape(Q, D)
+            parity["vs_single_gpu"] = {"what": "all %d rows: N-sharded result vs the same projection over the full bank on rank 0" % Q,
+                                       "max_rel_diff_x0": float((got - ref1).abs().max() / ref1.abs().max())}
+            del full
+        parity["ok"] = bool(parity["max_rel_err_x0"] <= 1e-3 and parity.get("vs_single_gpu", {}).get("max_rel_diff_x0", 0.0) <= 1e-3)
+
+    # ---- per-kernel times of the step itself: the library's own CUDA events around every kernel it launches
+    # ---- (sdn_profile_*), with the step replayed from a CUDA graph captured while profiling is on
     kernel_ms = {}
     nv.profile_enable(True)
-    L, st = nv.lib(), nv.current_stream()
-    xf = x.view(Q, D)
 
-    def stage_once():
-        # query prepare is not part of the stage; the events p0/p1 and the library's per-kernel events bracket
-        # sdn_repel_partial only
-        nv.check(L.sdn_query_prepare(nv.ptr(xf), None, 1.0, 0.0, Q, D, normalize, None,
-                                     nv.ptr(s.xq) if normalize else None, nv.ptr(s.xsq), nv.current_stream()))
-        query = s.xq if normalize else xf
-        nv.check(L.sdn_repel_partial(nv.ptr(bank.flat), nv.ptr(bank.sqnorm), nv.ptr(bank.planes), bank.N, D,
-                                     nv.ptr(query), nv.ptr(s.xsq), Q, 1.0 / (2 * sigma * sigma), 1, 1.0,
-                                     nv.ptr(s.num), nv.ptr(s.z), None, nv.ptr(s.ws), s.ws_bytes, args.path,
-                                     nv.current_stream()))
+    def prof_step():
+        proj.correct(x, sigma, scale, eps, normalize_channels=normalize, want_num=False, gate_threshold=gate)
 
-    # Replay the stage from a CUDA graph (the library's event records become graph nodes): the per-kernel intervals
-    # then contain ~1 us of dependency latency instead of an eager launch gap of 5-10 us.  Eager fallback if the
-    # capture is refused.
-    stage_graph = None
-    if not args.no_graph:
+    prof_graph = None
+    if use_graph and (world == 1 or proj.fused_merge):
         try:
-            stage_once()
+            x.copy_(x_src)
+            prof_step()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                stage_once()
+                prof_step()
             g.replay()
             torch.cuda.synchronize()
             if nv.profile_read():
-                stage_graph = g
+                prof_graph = g
         except Exception:
-            stage_graph = None
+            prof_graph = None
             torch.cuda.synchronize()
-    for i in range(args.steps):
+    barrier()
+    prof_steps = min(args.steps, 50)
+    for i in range(prof_steps):
+        x.copy_(x_src)
         flush_l2()
-        p0[i].record()
-        if stage_graph is not None:
-            stage_graph.replay()
+        if prof_graph is not None:
+            prof_graph.replay()
         else:
-            stage_once()
-        p1[i].record()
+            prof_step()
         for name, ms in nv.profile_read():
             kernel_ms.setdefault(name, []).append(ms)
-    torch.cuda.synchronize()
+    barrier()
     nv.profile_enable(False)
-    part_ms = sorted(a.elapsed_time(b) for a, b in zip(p0, p1))
-    part_avg_ms = sum(part_ms) / len(part_ms)
     kernel_avg = {k: sum(v) / len(v) for k, v in kernel_ms.items()}
     sampler.stop()
 
@@ -351,9 +394,10 @@ def main():
         if world == 1:
             conditioning_host(bank, xh, dh, sigma, scale, eps, normalize_channels=normalize, path=args.path)
         else:
-            x.copy_(xh, non_blocking=True)
-            proj.correct(x, sigma, scale, eps, normalize_channels=normalize)
-            xh.copy_(x, non_blocking=True)
+            # the same graphed N-sharded step as the timed region, fed from and drained to pinned host memory
+            x.copy_(xh.view_as(x), non_blocking=True)
+            step()
+            xh.copy_(x.view_as(xh), non_blocking=True)
             dh.copy_(proj._get(Q, False).denom, non_blocking=True)
             torch.cuda.synchronize()
 
@@ -365,7 +409,7 @@ def main():
     for _ in range(e2e_steps):
         xh.copy_(xh_src)
         flush_l2()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         e2e_step()
         e2e_total += time.perf_counter() - t0
@@ -373,6 +417,32 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = Q * e2e_steps / float(te.item())
+
+    # ---- the one-HBM-pass kernel on the same workload (one GPU, shapes it takes): timed next to the default path
+    one_pass = None
+    if world == 1 and args.path == 0 and normalize == 0 and nv.lib().sdn_repel_path(Q, bank.N, D, 1, nv.PATH_FLASH) == nv.PATH_FLASH \
+            and D % 1024 == 0 and 8192 <= D <= 16384 and Q > 8:
+        pf = Projector(bank, path=nv.PATH_FLASH)
+        xo = x_src.clone()
+        try:
+            for _ in range(3):
+                xo.copy_(x_src)
+                pf.correct_graphed(xo, sigma, scale, eps, want_num=False, gate_threshold=gate)
+            torch.cuda.synchronize()
+            o0 = [torch.cuda.Event(enable_timing=True) for _ in range(prof_steps)]
+            o1 = [torch.cuda.Event(enable_timing=True) for _ in range(prof_steps)]
+            for i in range(prof_steps):
+                xo.copy_(x_src)
+                flush_l2()
+                o0[i].record()
+                pf.correct_graphed(xo, sigma, scale, eps, want_num=False, gate_threshold=gate)
+                o1[i].record()
+            torch.cuda.synchronize()
+            oms = sorted(a.elapsed_time(b) for a, b in zip(o0, o1))
+            one_pass = {"kernel": "k_flash (SDN_PATH_FLASH, opt-in)", "ms_per_step": sum(oms) / len(oms), "p50_ms": oms[len(oms) // 2],
+                        "max_rel_diff_x0_vs_default_path": float((xo.reshape(Q, D) - got).abs().max() / got.abs().max())}
+        except RuntimeError as e:
+            one_pass = {"error": str(e)[:200]}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -383,64 +453,69 @@ def main():
         n_local = hi - lo
         npad = (n_local + 127) // 128 * 128
         bank_bytes = n_local * D * (2 if args.path == 4 else 4)   # fp32 bank == bf16 hi+lo planes: 4 B per element
-        stage_bytes = bank_bytes + n_local * 4 + 2 * Q * D * 4   # one pass over the bank
-        # algorithmic bytes of each kernel of the stage (what it must read + write once)
+        step_bytes = bank_bytes + n_local * 4 + 2 * Q * D * 4    # ONE pass over the (shard of the) bank + x0 in + x0' out
+        # algorithmic bytes of each kernel (what it must read + write once)
         kbytes = {
-            "k_stream": stage_bytes,
-            "k_stream_reduce": 2 * Q * D * 4,
-            "k_umma_xprep": Q * D * 4 + 128 * D * 2,
+            "k_stream": step_bytes, "k_stream_reduce": 2 * Q * D * 4, "k_stream_reduce_correct": 3 * Q * D * 4,
+            "k_umma_xprep": Q * D * 4 + 128 * D * 2, "k_umma_qprep": Q * D * 4 + 128 * D * 2,
             "k_umma_dots": bank_bytes + 128 * D * 2 + npad * 128 * 4,
             "k_umma_weights": npad * 128 * 4 + 128 * npad * 2,
-            "k_umma_accum": bank_bytes + 128 * npad * 2 + Q * D * 4,
-            "k_dots": bank_bytes + Q * D * 4 + Q * n_local * 4,
-            "k_weights": 2 * Q * n_local * 4,
+            "k_umma_listed_accum": 0,
+            "k_umma_accum": bank_bytes + 128 * npad * 2 + 2 * Q * D * 4,
+            "k_flash": step_bytes,
+            "k_dots": bank_bytes + Q * D * 4 + Q * n_local * 4, "k_weights": 2 * Q * n_local * 4,
             "k_accum": bank_bytes + Q * n_local * 4 + Q * D * 4,
+            "k_shard_merge_correct": (Q * D * 4 // max(1, world)) * (world + 1) + Q * D * 4,
         }
-        dom = max(kernel_avg, key=kernel_avg.get) if kernel_avg else None
-        if dom is not None:
-            dom_ms = kernel_avg[dom]
-            dom_bytes = kbytes.get(dom, stage_bytes)
-        else:
-            dom, dom_ms, dom_bytes = "sdn_repel_partial", part_avg_ms, stage_bytes
-        # DRAM bytes of that kernel from the committed `ncu --set full` capture of the same workload, if any
-        traffic, traffic_src = None, None
+        traffic_db = {}
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath) and world == 1:
-            ent = json.load(open(tpath)).get(f"{args.workload}/{dom}")
-            if ent:
-                traffic, traffic_src = ent["bytes"], ent["source"]
-        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        stage_achieved = stage_bytes / (part_avg_ms * 1e-3) / 1e9
+        if os.path.exists(tpath):
+            traffic_db = json.load(open(tpath))
+        kernels = {}
+        for k, ms in kernel_avg.items():
+            ent = traffic_db.get(f"{args.workload}/{k}") if world == 1 else None
+            b = kbytes.get(k)
+            kernels[k] = {"avg_ms": round(ms, 5), "algorithmic_bytes": b,
+                          "achieved_gbs": (b / (ms * 1e-3) / 1e9) if b else None,
+                          "frac": (b / (ms * 1e-3) / 1e9 / peak) if b else None,
+                          "traffic": ent["bytes"] if ent else None, "traffic_source": ent["source"] if ent else None}
+        dom = max(kernel_avg, key=kernel_avg.get) if kernel_avg else None
+        achieved = step_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic_sum = sum(v["traffic"] for v in kernels.values() if v["traffic"]) or None
+        if one_pass and "ms_per_step" in one_pass:
+            ent = traffic_db.get(f"{args.workload}/k_flash")
+            one_pass.update({"frac": step_bytes / (one_pass["ms_per_step"] * 1e-3) / 1e9 / peak,
+                             "traffic": ent["bytes"] if ent else None, "traffic_source": ent["source"] if ent else None})
         line = dict(base)
         line["config"] = dict(base["config"],
                               l2="flushed between steps outside the per-step events: 256 MiB memset, then a 256 MiB read so that no dirty lines are left",
-                              timing="sum of per-step CUDA-event intervals, max over ranks",
+                              timing="per-step CUDA-event intervals, max over ranks per step, summed",
                               kernel_path=args.path,
                               accumulate_pass="block-sparse (rows below fp32 resolution skipped)" if args.sparse
                               else "dense (every bank row read; the library default would skip negligible rows)",
                               launch="one CUDA graph replay per step (kernels captured from the eager call)"
                               if use_graph else "eager launches",
                               e2e_call="sdn_conditioning_host (C ABI, pinned host buffers)" if world == 1
-                              else "pinned host -> Projector.correct (N-sharded) -> pinned host",
+                              else "pinned host -> graphed N-sharded step (fused NVLink merge) -> pinned host",
                               shard_merge=("fused peer-memory kernel (reduce-scatter + correction + all-gather over NVLink)"
                                            if proj.fused_merge else f"NCCL all-reduce ({proj.fused_merge_error})")
                               if world > 1 else None)
         line.update({
             "value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
+            "step_ms": {"p50": pct(0.5), "p95": pct(0.95), "max": step_sorted[-1], "min": step_sorted[0]},
             "e2e": {"value": e2e_value, "unit": "projections/s", "h2d_bytes_per_step": Q * D * 4,
                     "d2h_bytes_per_step": Q * D * 4 + Q * 4, "steps": e2e_steps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": dom, "algorithmic_bytes": dom_bytes, "avg_ms": dom_ms,
-                         "share_of_stage": dom_ms / part_avg_ms,
+            "parity_check": parity,
+            "roofline": {"bound": "hbm",
+                         "what": "the whole step: SURVEY 8(d) bytes of ONE pass over the bank (N*D*4 + N*4 + 2*Q*D*4 per GPU) / ms_per_step",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes": step_bytes, "traffic": traffic_sum,
+                         "traffic_note": "sum of the measured DRAM bytes (ncu dram__bytes_read+write) of the step's kernels that have a capture under profiles/",
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "kernels_ms": {k: round(v, 5) for k, v in kernel_avg.items()},
-                         "kernel_timing": "library CUDA events around each kernel, stage replayed from a CUDA graph"
-                         if stage_graph is not None else "library CUDA events around each kernel, eager launches",
-                         "stage": {"what": "sdn_repel_partial: every kernel of the bank-streaming stage, against "
-                                           "ONE pass over the bank (N*D*4 + N*4 + 2*Q*D*4 bytes)",
-                                   "algorithmic_bytes": stage_bytes, "avg_ms": part_avg_ms, "min_ms": part_ms[0],
-                                   "achieved": stage_achieved, "frac": stage_achieved / peak}},
+                         "dominant_kernel": dom, "kernels": kernels,
+                         "kernel_timing": "library CUDA events around each kernel, step replayed from a CUDA graph"
+                         if prof_graph is not None else "library CUDA events around each kernel, eager launches",
+                         "one_pass": one_pass},
             "clocks": sampler.summary(),
         })
         if not args.no_cpu_baseline and world == 1:

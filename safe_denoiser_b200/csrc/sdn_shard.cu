@@ -153,7 +153,9 @@ extern "C" int sdn_shard_merge_correct(const void* const* peer_packed, void* con
   a.counter = static_cast<unsigned int*>(counter);
   const int64_t slice_v = D / 4 / world + 1;
   const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(slice_v, 256), 1024));
+  const int pid = g_prof.begin("k_shard_merge_correct", (cudaStream_t)stream);
   k_shard_merge_correct<<<dim3(gx, (unsigned)Q), 256, 0, (cudaStream_t)stream>>>(a);
+  g_prof.end(pid, (cudaStream_t)stream);
   SDN_LAUNCHED();
   return SDN_OK;
 }
