@@ -231,8 +231,10 @@ int sdn_conditioning_fused(const float* bank, const float* sqnorm, const void* p
  * all peer-mapped in this process (CUDA IPC / symmetric memory).  Rank `rank` reduces D-slice `rank` over all peers
  * in rank order, applies x0' = x0 - scale * num / (sum_p z_p + eps) and stores the slice into every rank's result
  * buffer.  `epoch_word` is a local device uint32 initialised to 1 on every rank; the kernel reads the epoch of the
- * launch from it and advances it, so the call can be replayed from a CUDA graph.  `counter` is a local zeroed uint32.
- * Every rank must launch the call; waits are bounded (trap after ~seconds). */
+ * launch from it and advances it, so the call can be replayed from a CUDA graph.  `counter` is a local zeroed uint32 [4]:
+ * word 0 is scratch, word 1 a sticky error flag the kernel raises when a peer did not show up within
+ * SDN_SHARD_TIMEOUT_S seconds (default 60; a late host only delays the others, nothing traps) -- the result of that
+ * step is then undefined and the caller should stop using the link.  Every rank must launch the call. */
 int sdn_shard_merge_correct(const void* const* peer_packed, void* const* peer_out, void* const* peer_sig,
                             int32_t rank, int32_t world, void* epoch_word, int64_t Q, int64_t D,
                             float eps, float scale, float gate_threshold, int32_t flags,
@@ -251,6 +253,15 @@ int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t 
                      float radius, float scale,
                      float* term_out, float* wsum_out,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same in two steps, for N-sharded banks: un-normalised sums over this shard's rows
+ *   num_out [Q,D] = sum_i w_i n_i ,  wsum_out [Q] = sum_i w_i ,  w_i = relu(radius/d_qi - 1)
+ * (all-reduce both over the ranks), then term = wsum * xq - num ; x0_inout += scale * term (term_out optional). */
+int sdn_sparse_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D,
+                       const float* xq, const float* xsq, int64_t Q, float radius,
+                       float* num_out, float* wsum_out, void* workspace, size_t workspace_bytes, void* stream);
+int sdn_sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale,
+                     const float* xq, float* x0_inout, float* term_out, void* stream);
 
 /* ---- host-buffer convenience: the e2e path ------------------------------------------------
  * One conditioning() call with HOST tensors: H2D of x0_host [Q,D], projection over a device-resident

@@ -86,6 +86,31 @@ def closed_form(x, bank, sigma=1.0, eps=1e-8, dist_power=1, bank_alpha=1.0,
     }
 
 
+def closed_form_chunked(x, bank, sigma=1.0, eps=1e-8, chunk=2048, weight_rows=()):
+    """closed_form for banks too large for float64 copies (BASELINE configs[4]: N = 30 000 .. 200 000): the bank rows
+    are taken ``chunk`` at a time (float64 temporaries [chunk, D] and [Q, chunk]); same arithmetic, dist_power 1.
+    Returns float64 Z [Q], denom [Q], num [Q,D], neg [Q,D] and k [len(weight_rows), N] for the listed query rows."""
+    xf = _flat64(x)
+    bank = np.asarray(bank)
+    n = bank.shape[0]
+    q, d = xf.shape
+    xs = (xf * xf).sum(1)
+    Z = np.zeros(q)
+    num = np.zeros((q, d))
+    rows = list(weight_rows)
+    k_rows = np.zeros((len(rows), n))
+    for lo in range(0, n, chunk):
+        bf = bank[lo:lo + chunk].reshape(min(chunk, n - lo), -1).astype(np.float64)
+        d2 = np.maximum(xs[:, None] + (bf * bf).sum(1)[None, :] - 2.0 * (xf @ bf.T), 0.0)
+        k = np.exp(-np.sqrt(d2) / (2.0 * float(sigma) ** 2))
+        Z += k.sum(1)
+        num += k @ bf
+        if rows:
+            k_rows[:, lo:lo + bf.shape[0]] = k[rows]
+    denom = Z + eps
+    return {"Z": Z, "denom": denom, "num": num, "neg": num / denom[:, None], "k": k_rows}
+
+
 def conditioning_fast(x4, bank4, scale=1.0, eps=1e-8, sigma=1.0, sdv3=False):
     """fast.py:120-132 (sdv3: fast_sdv3.py:120-132).
 

@@ -38,12 +38,16 @@ def ddpm_timesteps(num_inference_steps=50, num_train_timesteps=1000, steps_offse
     return (np.arange(num_inference_steps) * ratio).round()[::-1].astype(np.int64) + steps_offset
 
 
-def ddpm_coefficients(alphas_cumprod, t, num_inference_steps=50):
-    """All scalars one in-window DDPM step needs."""
+def ddpm_coefficients(alphas_cumprod, t, num_inference_steps=50, final_alpha_cumprod=None):
+    """All scalars one in-window DDPM step needs.  At the last step DDPMScheduler takes alpha_bar_prev = 1,
+    DDIMScheduler its final_alpha_cumprod (= alphas_cumprod[0] for the SD-1.4 config, set_alpha_to_one = False):
+    the two *_prev entries used by the DDIM step follow the latter."""
     T = len(alphas_cumprod)
     t_prev = t - T // num_inference_steps
     ab_t = float(alphas_cumprod[t])
     ab_prev = float(alphas_cumprod[t_prev]) if t_prev >= 0 else 1.0
+    fin = float(alphas_cumprod[0]) if final_alpha_cumprod is None else float(final_alpha_cumprod)
+    ab_prev_ddim = float(alphas_cumprod[t_prev]) if t_prev >= 0 else fin
     a_t = ab_t / ab_prev
     b_t = 1.0 - a_t
     var = max((1.0 - ab_prev) / (1.0 - ab_t) * b_t, 1e-20)
@@ -52,7 +56,7 @@ def ddpm_coefficients(alphas_cumprod, t, num_inference_steps=50):
         "c_x0": (ab_prev ** 0.5) * b_t / (1.0 - ab_t),
         "c_xt": (a_t ** 0.5) * (1.0 - ab_prev) / (1.0 - ab_t),
         "sigma_noise": (var ** 0.5) if t > 0 else 0.0,
-        "sqrt_ab_prev": ab_prev ** 0.5, "sqrt_1m_ab_prev": (1.0 - ab_prev) ** 0.5,
+        "sqrt_ab_prev": ab_prev_ddim ** 0.5, "sqrt_1m_ab_prev": (1.0 - ab_prev_ddim) ** 0.5,
     }
 
 

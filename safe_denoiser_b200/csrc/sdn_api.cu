@@ -221,6 +221,31 @@ int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t 
   return sparse_apply(num, wsum_out, Q, D, scale, query, x0_inout, term_out, st);
 }
 
+int sdn_sparse_partial(const float* bank, const float* sqnorm, int64_t N, int64_t D, const float* xq, const float* xsq,
+                       int64_t Q, float radius, float* num_out, float* wsum_out, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (!bank || !sqnorm || !xq || !xsq || !num_out || !wsum_out || !workspace) return SDN_E_NULL;
+  if (Q <= 0 || N <= 0 || D <= 0 || Q > 65535) return SDN_E_SHAPE;
+  if (D % 4 != 0 || !aligned16(bank) || !aligned16(xq) || !aligned16(num_out)) return SDN_E_ALIGN;
+  if (workspace_bytes < generic_workspace_bytes(Q, N)) return SDN_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* S = static_cast<float*>(workspace);
+  int rc = generic_dots(bank, N, D, xq, Q, S, st);
+  if (rc) return rc;
+  rc = sparse_weights(S, sqnorm, xsq, Q, N, radius, wsum_out, st);
+  if (rc) return rc;
+  return generic_accum(bank, N, D, S, Q, num_out, st);
+}
+
+int sdn_sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale, const float* xq,
+                     float* x0_inout, float* term_out, void* stream) {
+  if (!num || !wsum || !xq || !x0_inout) return SDN_E_NULL;
+  if (Q <= 0 || D <= 0) return SDN_E_SHAPE;
+  if (D % 4 != 0 || !aligned16(num) || !aligned16(xq) || !aligned16(x0_inout) || (term_out && !aligned16(term_out)))
+    return SDN_E_ALIGN;
+  return sparse_apply(num, wsum, Q, D, scale, xq, x0_inout, term_out, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ host-buffer path (e2e)
 namespace {
 struct HostCache {

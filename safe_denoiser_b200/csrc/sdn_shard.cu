@@ -8,8 +8,9 @@
 //                        store x0'[q][d] into EVERY rank's output buffer (peer stores)
 // so each element crosses NVLink once in and once out -- a two-shot all-reduce with the epilogue in the middle.
 // Cross-GPU ordering uses epoch flags in peer-mapped memory (release/acquire at system scope); every wait is
-// bounded and traps instead of hanging the GPU.  One kernel per rank, each on its own GPU.
+// bounded by a wall-clock timeout that raises an error flag (no trap).  One kernel per rank, each on its own GPU.
 #include <algorithm>
+#include <cstdlib>
 
 #include "sdn_internal.h"
 
@@ -29,7 +30,8 @@ struct MergeArgs {
   const float* x0;                  // local replicated query [Q,D]
   float* denom_out;                 // local [Q]
   int32_t* gate_out;                // local [Q]
-  unsigned int* counter;            // local, zero between launches
+  unsigned int* counter;            // local [4]: [0] block counter (zero between launches), [1] sticky error flag
+  unsigned long long timeout_ns;    // how long a rank waits for a peer before it gives up (error flag, no trap)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -40,12 +42,25 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// epochs only grow; compare with wrap-around in mind
-__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t epoch) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// epochs only grow; compare with wrap-around in mind.  A peer whose host is late (image save, GC, torch.load)
+// only delays this rank; after `timeout_ns` (default 60 s, SDN_SHARD_TIMEOUT_S) the rank stops waiting, raises
+// the sticky error flag and lets the kernel finish -- a trap would kill the CUDA context of a healthy rank.
+__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t epoch, unsigned long long timeout_ns,
+                                           unsigned int* err_flag) {
+  unsigned long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
     if ((int32_t)(ld_acquire_sys(p) - epoch) >= 0) return;
-    if (spin > 64u) __nanosleep(64);
-    if (spin > (1u << 22)) __trap();   // seconds: a missing peer must not hang this GPU
+    if (spin > 64u) __nanosleep(spin > 4096u ? 1000 : 64);
+    if ((spin & 1023u) == 1023u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) { atomicExch(err_flag, 1u); return; }
+    }
   }
 }
 
@@ -63,7 +78,7 @@ __global__ void __launch_bounds__(256) k_shard_merge_correct(const MergeArgs a) 
     __threadfence_system();
     st_release_sys(a.sig[tid] + a.rank, epoch);
   }
-  if (tid < a.world) spin_until(a.sig[a.rank] + tid, epoch);
+  if (tid < a.world) spin_until(a.sig[a.rank] + tid, epoch, a.timeout_ns, a.counter + 1);
   __syncthreads();
 
   if (tid == 0) {
@@ -117,7 +132,7 @@ __global__ void __launch_bounds__(256) k_shard_merge_correct(const MergeArgs a) 
     if (tid < a.world) {
       __threadfence_system();
       st_release_sys(a.sig[tid] + kMaxRanks + a.rank, epoch);
-      spin_until(a.sig[a.rank] + kMaxRanks + tid, epoch);
+      spin_until(a.sig[a.rank] + kMaxRanks + tid, epoch, a.timeout_ns, a.counter + 1);
     }
     __syncthreads();
     if (tid == 0) {
@@ -151,6 +166,12 @@ extern "C" int sdn_shard_merge_correct(const void* const* peer_packed, void* con
   a.rank = rank; a.world = world; a.epoch_ptr = static_cast<uint32_t*>(epoch_word); a.Q = Q; a.D = D; a.eps = eps; a.scale = scale;
   a.gate_thr = gate_threshold; a.flags = flags; a.x0 = x0_local; a.denom_out = denom_out; a.gate_out = gate_out;
   a.counter = static_cast<unsigned int*>(counter);
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("SDN_SHARD_TIMEOUT_S");
+    const double sec = e ? atof(e) : 60.0;
+    return (unsigned long long)((sec > 0.0 ? sec : 60.0) * 1e9);
+  }();
+  a.timeout_ns = timeout_ns;
   const int64_t slice_v = D / 4 / world + 1;
   const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(slice_v, 256), 1024));
   const int pid = g_prof.begin("k_shard_merge_correct", (cudaStream_t)stream);

@@ -500,7 +500,7 @@ template <bool CHUNKED, int G>
 __global__ void __launch_bounds__(UCfg<G>::kThreads, 1)
 k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
              const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
-             int rblocks_total, int nsplit, int use_atomic, int use_lo, int p_group_rows, const int* rowflags,
+             int rblocks_total, int nsplit, int64_t split_stride, int use_lo, int p_group_rows, const int* rowflags,
              const int* __restrict__ list_count, const int* __restrict__ dense_flag, const AccumEpi epi) {
   using C = UCfg<G>;
   if (dense_flag && __ldg(dense_flag)) {
@@ -642,7 +642,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     const int g = (warp - 2) >> 2;
     const int Qg = min(kUQ, Q - g * kUQ);                         // query rows of this group (>= 1)
     const int64_t qoff = (int64_t)g * kUQ * D;
-    float* const numg = num ? num + qoff : nullptr;
+    // bank-row splits write their own partial [Q][D] (summed in split order by k_umma_splitsum): no atomics
+    float* const numg = num ? num + qoff + (int64_t)blockIdx.y * split_stride : nullptr;
     const float* const zg = epi.z ? epi.z + g * kUQ : nullptr;
     float* const x0g = epi.x0 ? epi.x0 + qoff : nullptr;
     float* const negg = epi.neg_out ? epi.neg_out + qoff : nullptr;
@@ -704,7 +705,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
           const int q = c * 32 + j;
           if (q < Qg) {
             float* o = numg + (int64_t)q * D + d;
-            if (use_atomic) atomicAdd(o, a[j] + b[j]); else *o = a[j] + b[j];
+            *o = a[j] + b[j];
           }
         }
       }
@@ -778,7 +779,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         for (int j = 0; j < kUQ; ++j) {
           if (j < Qg) {
             float* o = numg + (int64_t)j * D + d;
-            if (use_atomic) atomicAdd(o, sum[j]); else *o = sum[j];
+            *o = sum[j];
           }
         }
       }
@@ -797,6 +798,25 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     u_fence_after();
     u_tmem_dealloc(tmem, 2 * C::kAccCols);
   }
+}
+
+// num[q][d] = sum_s part[s][q][d] in split order (deterministic; the splits used to atomicAdd into num).  Exits like
+// k_umma_accum does when the listed accumulate already produced the result.
+__global__ void __launch_bounds__(256)
+k_umma_splitsum(const float* __restrict__ part, int nsplit, int64_t split_stride, int64_t QD, int Q, float* __restrict__ num,
+                const int* __restrict__ list_count, const int* __restrict__ dense_flag) {
+  if (dense_flag && __ldg(dense_flag)) {
+  } else if (list_count && siglist_all_short(list_count, Q)) {
+    return;
+  }
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i >= QD) return;
+  float4 s4 = *reinterpret_cast<const float4*>(part + i);
+  for (int sp = 1; sp < nsplit; ++sp) {
+    const float4 p = *reinterpret_cast<const float4*>(part + (int64_t)sp * split_stride + i);
+    s4.x += p.x; s4.y += p.y; s4.z += p.z; s4.w += p.w;
+  }
+  *reinterpret_cast<float4*>(num + i) = s4;
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -851,7 +871,8 @@ struct UmmaLayout {
   int ksplit;
   int nflags;          // row blocks of 64 bank rows
   int xsq_nparts;
-  size_t off_x, off_s, off_p, off_z, off_f, off_q, total;
+  size_t off_x, off_s, off_p, off_z, off_f, off_q, off_n, total;
+  int nsplit;          // bank-row splits of phase B (partials in the workspace, summed in order)
   // per-group strides (elements)
   int64_t split_stride, zpart_stride;
 };
@@ -878,6 +899,12 @@ UmmaLayout umma_layout(int64_t Q, int64_t N, int64_t D) {
   L.off_f = o; o += (size_t)L.nflags * 4 + G * kUQ * 4 + G * kUQ * 4 + 16 + G * kUQ * kListCap * 8 + 256;
   o = (o + 255) / 256 * 256;
   L.off_q = o; o += G * L.xsq_nparts * kUQ * 4;              // ||x||^2 partials of the fused query prepare
+  o = (o + 255) / 256 * 256;
+  {
+    const int dblocks = (int)(D / kUDBlock), rblocks = (int)(L.npad / kUK);
+    L.nsplit = std::max(1, std::min(rblocks / 8, kNumSMs / std::max(1, dblocks)));
+  }
+  L.off_n = o; o += L.nsplit > 1 ? (size_t)L.nsplit * (size_t)Q * D * 4 : 0;   // phase-B split partials [nsplit][Q][D]
   L.total = (o + 255) / 256 * 256;
   return L;
 }
@@ -952,7 +979,7 @@ int configure_kernels() {
 
 struct AccumLaunch {
   CUtensorMap tm_p, tm_hi, tm_lo;
-  float* num; int64_t D; int Q, rblocks, nsplit, use_atomic, use_lo, p_group_rows;
+  float* num; int64_t D; int64_t split_stride; int Q, rblocks, nsplit, use_lo, p_group_rows;
   const int* flags; const int* count; const int* dense;
   AccumEpi e;
   int gridx; bool chunked;
@@ -962,11 +989,11 @@ void launch_accum(const AccumLaunch& a, cudaStream_t st) {
   const dim3 grid(a.gridx, a.nsplit);
   if (a.chunked)
     k_umma_accum<true, G><<<grid, UCfg<G>::kThreads, kUSmemBytes, st>>>(a.tm_p, a.tm_hi, a.tm_lo, a.num, a.D, a.Q, a.rblocks,
-                                                                      a.nsplit, a.use_atomic, a.use_lo, a.p_group_rows,
+                                                                      a.nsplit, a.split_stride, a.use_lo, a.p_group_rows,
                                                                       a.flags, a.count, a.dense, a.e);
   else
     k_umma_accum<false, G><<<grid, UCfg<G>::kThreads, kUSmemBytes, st>>>(a.tm_p, a.tm_hi, a.tm_lo, a.num, a.D, a.Q, a.rblocks,
-                                                                       a.nsplit, a.use_atomic, a.use_lo, a.p_group_rows,
+                                                                       a.nsplit, a.split_stride, a.use_lo, a.p_group_rows,
                                                                        a.flags, a.count, a.dense, a.e);
 }
 }  // namespace
@@ -994,25 +1021,42 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   const __nv_bfloat16* hi = static_cast<const __nv_bfloat16*>(planes);
   const __nv_bfloat16* lo = hi + N * D;
 
-  // tensor maps depend only on (planes, workspace, N, D, G): re-encode when one of those changes
-  struct MapCache { const void* planes; const void* ws; int64_t N, D; int G; CUtensorMap m[6]; bool valid; };
-  static MapCache cache{nullptr, nullptr, 0, 0, 0, {}, false};
+  // tensor maps depend only on (device, planes, workspace, N, D, G): a small per-process cache (several projectors /
+  // devices in one process each keep their entry; least recently used is replaced)
+  struct MapCache { int dev; const void* planes; const void* ws; int64_t N, D; int G; CUtensorMap m[6]; uint64_t stamp; };
+  static MapCache cache[8];
+  static int cache_n = 0;
+  static uint64_t cache_clock = 0;
   static std::mutex cache_mu;
   CUtensorMap tm_x, tm_hiA, tm_loA, tm_p, tm_hiB, tm_loB;
   {
     std::lock_guard<std::mutex> lk(cache_mu);
-    if (!(cache.valid && cache.planes == planes && cache.ws == ws && cache.N == N && cache.D == D && cache.G == G)) {
+    MapCache* hit = nullptr;
+    for (int i = 0; i < cache_n && !hit; ++i)
+      if (cache[i].dev == dev && cache[i].planes == planes && cache[i].ws == ws && cache[i].N == N && cache[i].D == D && cache[i].G == G)
+        hit = &cache[i];
+    if (!hit) {
+      MapCache c{};
       int rc;
-      cache.valid = false;
-      if ((rc = make_map(&cache.m[0], xpl, (uint64_t)G * kUStack, D, kUStack, kUK))) return rc;
-      if ((rc = make_map(&cache.m[1], hi, N, D, kUBankTile, kUK))) return rc;
-      if ((rc = make_map(&cache.m[2], lo, N, D, kUBankTile, kUK))) return rc;
-      if ((rc = make_map(&cache.m[3], P, (uint64_t)G * L.npad, kUStack, kUK, 64))) return rc;
-      if ((rc = make_map(&cache.m[4], hi, N, D, kUK, 64))) return rc;
-      if ((rc = make_map(&cache.m[5], lo, N, D, kUK, 64))) return rc;
-      cache.planes = planes; cache.ws = ws; cache.N = N; cache.D = D; cache.G = G; cache.valid = true;
+      if ((rc = make_map(&c.m[0], xpl, (uint64_t)G * kUStack, D, kUStack, kUK))) return rc;
+      if ((rc = make_map(&c.m[1], hi, N, D, kUBankTile, kUK))) return rc;
+      if ((rc = make_map(&c.m[2], lo, N, D, kUBankTile, kUK))) return rc;
+      if ((rc = make_map(&c.m[3], P, (uint64_t)G * L.npad, kUStack, kUK, 64))) return rc;
+      if ((rc = make_map(&c.m[4], hi, N, D, kUK, 64))) return rc;
+      if ((rc = make_map(&c.m[5], lo, N, D, kUK, 64))) return rc;
+      c.dev = dev; c.planes = planes; c.ws = ws; c.N = N; c.D = D; c.G = G;
+      int slot = cache_n;
+      if (cache_n == 8) {
+        slot = 0;
+        for (int i = 1; i < 8; ++i) if (cache[i].stamp < cache[slot].stamp) slot = i;
+      } else {
+        ++cache_n;
+      }
+      cache[slot] = c;
+      hit = &cache[slot];
     }
-    tm_x = cache.m[0]; tm_hiA = cache.m[1]; tm_loA = cache.m[2]; tm_p = cache.m[3]; tm_hiB = cache.m[4]; tm_loB = cache.m[5];
+    hit->stamp = ++cache_clock;
+    tm_x = hit->m[0]; tm_hiA = hit->m[1]; tm_loA = hit->m[2]; tm_p = hit->m[3]; tm_hiB = hit->m[4]; tm_loB = hit->m[5];
   }
 
   // significant-row lists, shared by the groups of the pass (flags and the dense mark are unions over the groups;
@@ -1091,13 +1135,13 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   // phase B: one CTA per 128 d, bank rows split when that leaves SMs idle
   const int dblocks = (int)(D / kUDBlock);
   const int rblocks = (int)(L.npad / kUK);
-  int nsplit = std::max(1, std::min(rblocks / 8, kNumSMs / dblocks));
+  const int nsplit = L.nsplit;
   AccumEpi e{};
   if (epi) {
     if (nsplit != 1) return SDN_E_UNSUPPORTED;
     e = *epi;
   }
-  if (nsplit > 1 && num) SDN_CUDA_OK(cudaMemsetAsync(num, 0, sizeof(float) * Q * D, st));
+  float* const part = reinterpret_cast<float*>(w + L.off_n);
   if (sparse) {
     pid = g_prof.begin("k_umma_listed_accum", st);
     k_umma_listed_accum<<<dim3((unsigned)cdiv(D, 1024), (unsigned)Q), 256, 0, st>>>(
@@ -1108,8 +1152,8 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   }
   pid = g_prof.begin("k_umma_accum", st);
   AccumLaunch al{};
-  al.tm_p = tm_p; al.tm_hi = tm_hiB; al.tm_lo = tm_loB; al.num = num; al.D = D; al.Q = (int)Q; al.rblocks = rblocks;
-  al.nsplit = nsplit; al.use_atomic = nsplit > 1 ? 1 : 0; al.use_lo = bf16_bank ? 0 : 1; al.p_group_rows = (int)L.npad;
+  al.tm_p = tm_p; al.tm_hi = tm_hiB; al.tm_lo = tm_loB; al.num = nsplit > 1 ? part : num; al.D = D; al.Q = (int)Q; al.rblocks = rblocks;
+  al.nsplit = nsplit; al.split_stride = nsplit > 1 ? Q * D : 0; al.use_lo = bf16_bank ? 0 : 1; al.p_group_rows = (int)L.npad;
   al.flags = sparse ? lists.flags : nullptr; al.count = sparse ? lists.count : nullptr;
   al.dense = sparse ? lists.dense : nullptr; al.e = e;
   al.gridx = nsplit == 1 ? std::min(dblocks, kNumSMs) : dblocks;
@@ -1118,6 +1162,13 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   if (G == 1) launch_accum<1>(al, st); else launch_accum<2>(al, st);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
+  if (nsplit > 1) {
+    pid = g_prof.begin("k_umma_splitsum", st);
+    k_umma_splitsum<<<(unsigned)cdiv(Q * D, 1024), 256, 0, st>>>(part, nsplit, Q * D, Q * D, (int)Q, num,
+                                                                  sparse ? lists.count : nullptr, sparse ? lists.dense : nullptr);
+    g_prof.end(pid, st);
+    SDN_LAUNCHED();
+  }
   return SDN_OK;
 }
 

@@ -150,11 +150,19 @@ class Projector:
             s = _Scratch()
             s.link = None
             if self.group is not None and self.fused_merge:
+                import torch.distributed as dist
                 try:
                     s.link = ShardLink(Q, D, self.group, dev)
                 except Exception as e:           # no peer mapping on this box: NCCL all-reduce instead
-                    self.fused_merge = False
                     self.fused_merge_error = repr(e)
+                # every rank must take the same exchange (a rank in the peer kernel and a rank in all_reduce
+                # would wait for each other forever): agree on the outcome of the rendezvous
+                ok = torch.tensor([1 if s.link is not None else 0], dtype=torch.int32, device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+                if int(ok.item()) == 0:
+                    s.link = None
+                    self.fused_merge = False
+                    self.fused_merge_error = self.fused_merge_error or "a peer rank could not map the buffers"
             # num and z live in one packed [Q, D+1]-sized buffer so the N-shard merge is ONE exchange
             s.packed = s.link.packed if s.link is not None else torch.empty(Q * D + Q, dtype=torch.float32, device=dev)
             s.num = s.packed[: Q * D].view(Q, D)
@@ -220,6 +228,14 @@ class Projector:
             query = s.xq
         elif xo is not None:
             query = xo
+        elif not plain:
+            # a combined query (c_x * x + c_m * model_out) with no caller buffer for it: it must exist somewhere,
+            # the distances are taken on it, not on the raw input
+            if s.xq is None:
+                s.xq = torch.empty(Q, self.bank.D, dtype=torch.float32, device=self.bank.device)
+            nv.check(L.sdn_query_prepare(nv.ptr(xf), nv.ptr(mo), c_x, c_m, Q, self.bank.D, 0, nv.ptr(s.xq), None,
+                                         nv.ptr(s.xsq), st))
+            query = s.xq
         else:
             query = xf
         b = self.bank
@@ -295,6 +311,10 @@ class Projector:
         xf.copy_(merged)
         return s
 
+    def shard_error(self) -> bool:
+        """True when a merge kernel of this projector gave up waiting for a peer (sticky; synchronises)."""
+        return any(sc.link is not None and int(sc.link.counter[1].item()) != 0 for sc in self._scratch.values())
+
     def query_buffer(self, Q: int, shape=None) -> torch.Tensor:
         """N-sharded banks: a [Q, D] query tensor that lives in this rank's peer-mapped result buffer.  A query
         placed there is corrected in place by the merge kernel itself (rank r rewrites D-slice r on every rank), which
@@ -369,8 +389,10 @@ class Projector:
         return out.view_as(x_t), s
 
     def flow_step(self, x, v, zn, sigma_t: float, sigma_next: float, kernel_sigma: float, scale: float,
-                  eps: float, *, normalize_channels: int, x0c_out: torch.Tensor | None = None):
-        """One fused SD3 flow-matching step (safe_denoiser_pipeline.py:1142-1161).  fp32 in/out."""
+                  eps: float, *, normalize_channels: int, x0c_out: torch.Tensor | None = None,
+                  out_dtype: torch.dtype | None = None):
+        """One fused SD3 flow-matching step (safe_denoiser_pipeline.py:1141-1161).  fp32 in; the pipeline casts the
+        new latents back to its fp16 working dtype (:1161): pass ``out_dtype=torch.float16`` for that."""
         Q, xf = self._flat_query(x)
         s0 = self._get(Q, True)
         x0_tmp = None if normalize_channels > 0 else s0.xq   # un-normalised x0 is only the query
@@ -384,7 +406,8 @@ class Projector:
                                             nv.ptr(self._flat_query(zn)[1]), float(sigma_t), float(sigma_next),
                                             nv.ptr(out), nv.ptr(xc), nv.ptr(s.denom), nv.ptr(s.mean),
                                             nv.current_stream()))
-        return out.view_as(x), s
+        out = out.view_as(x)
+        return (out.to(out_dtype) if out_dtype is not None and out_dtype != out.dtype else out), s
 
     def sparse(self, x0: torch.Tensor, radius: float, scale: float, want_term: bool = False,
                normalize_channels: int = 0):
@@ -400,10 +423,21 @@ class Projector:
         need = Q * b.N * 4 + Q * b.D * 4 + 1024
         ws = torch.empty(need, dtype=torch.uint8, device=b.device)
         term = torch.empty_like(xf) if want_term else None
-        wsum = torch.empty(Q, dtype=torch.float32, device=b.device)
-        nv.check(L.sdn_sparse_repel(nv.ptr(b.flat), nv.ptr(b.sqnorm), b.N, b.D, nv.ptr(xf), nv.ptr(xq), nv.ptr(s.xsq), Q,
-                                    float(radius), float(scale), nv.ptr(term), nv.ptr(wsum),
-                                    nv.ptr(ws), need, st))
+        if self.group is None:
+            wsum = torch.empty(Q, dtype=torch.float32, device=b.device)
+            nv.check(L.sdn_sparse_repel(nv.ptr(b.flat), nv.ptr(b.sqnorm), b.N, b.D, nv.ptr(xf), nv.ptr(xq), nv.ptr(s.xsq), Q,
+                                        float(radius), float(scale), nv.ptr(term), nv.ptr(wsum),
+                                        nv.ptr(ws), need, st))
+            return term, wsum
+        # N-sharded bank: every rank sums its rows (sum_i w_i n_i and sum_i w_i), ONE all-reduce of the packed
+        # [Q*D | Q] buffer, then the same apply on every rank -- the force needs all rows of the bank
+        packed = torch.empty(Q * b.D + Q, dtype=torch.float32, device=b.device)
+        num, wsum = packed[: Q * b.D].view(Q, b.D), packed[Q * b.D:]
+        nv.check(L.sdn_sparse_partial(nv.ptr(b.flat), nv.ptr(b.sqnorm), b.N, b.D, nv.ptr(xq if xq is not None else xf),
+                                      nv.ptr(s.xsq), Q, float(radius), nv.ptr(num), nv.ptr(wsum), nv.ptr(ws), need, st))
+        merge_partials(packed, self.group)
+        nv.check(L.sdn_sparse_apply(nv.ptr(num), nv.ptr(wsum), Q, b.D, float(scale), nv.ptr(xq if xq is not None else xf),
+                                    nv.ptr(xf), nv.ptr(term), st))
         return term, wsum
 
 

@@ -36,7 +36,7 @@ class FastRepellencyMethod(RepellencyBase):
             if x_0_hat.dtype == torch.float32:
                 x_0_hat.copy_(q)                             # keep the in-place contract for strided input
             else:
-                x_0_hat = q
+                x_0_hat = q.to(x_0_hat.dtype)                # the reference hands back ref_data.dtype (fast.py:121-122)
         return x_0_hat, neg, s
 
     def conditioning_1(self, x_0_hat, **kwargs):

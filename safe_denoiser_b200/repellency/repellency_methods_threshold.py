@@ -150,7 +150,9 @@ class RBFKernelRepellency(_Calibrated):
             self.noisy_proj_refs = self._noisy_refs(kwargs)
             self.noisy_refs_beta_quantitle = self.empirical_beta(sigma=self.sigma, quantitle=self.quantile)
             last_t = list(self.noisy_refs_beta_quantitle.keys())[-1]
-            self.beta_threshold = self.noisy_refs_beta_quantitle[last_t]
+            # a python float once, here: the 0-d CUDA tensor torch.quantile returns would cost one device-to-host sync
+            # per sampling step in conditioning_threshold (the calibration prints .item() per level anyway)
+            self.beta_threshold = float(self.noisy_refs_beta_quantitle[last_t])
             del self.noisy_proj_refs, self.noisy_refs_beta_quantitle
             torch.cuda.empty_cache()
 

@@ -164,6 +164,48 @@ def sparse_sdv3_cases(out):
             out[key + "/item"] = np.float64(d["mean_x_0_hat"])
 
 
+def flow_step_cases(out):
+    """The SD3 caller epilogue: the reference pipeline cannot be imported (diffusers is absent), so the
+    lines of its in-window branch are text-extracted from models/sdv3/safe_denoiser_pipeline.py and EXECUTED here,
+    unmodified, around the reference's own fast_sdv3 processor -- fp16 latents as in the pipeline, including the
+    cast back to fp16 (:1161)."""
+    import math
+    src = open(os.path.join(REF, "models", "sdv3", "safe_denoiser_pipeline.py")).read().splitlines()
+    # :1141 "# current time step" ... :1161 "latents = latents.to(latents_dtype)"
+    first = next(i for i, l in enumerate(src) if l.strip() == "# current time step")
+    last = next(i for i, l in enumerate(src) if i > first and l.strip() == "latents = latents.to(latents_dtype)")
+    assert (first + 1, last + 1) == (1141, 1161), (first + 1, last + 1)
+    body = [l for l in src[first:last + 1]]
+    # the block spans two indentation levels (inside / after `if repellency_processor is not None:`) and holds only
+    # simple statements: left-strip every line (the continuation line of the conditioning(...) call sits in parentheses)
+    code = "\n".join(l.strip() for l in body)
+    c, h, w, n, q = 16, 8, 8, 40, 3
+    bank = synthetic_bank(n, c, h, w, seed=1234)
+    out["flow/bank"] = bank.numpy()
+    proc = build(ref_sdv3, "kernel_fast", bank, scale=0.03, sigma=3.55)
+    sig_list = [1.0, 0.98, 0.8, 0.78, 0.02]
+    for case, (i, steps) in enumerate(((0, 5), (2, 5), (4, 5))):       # the last one: sigma_next = 0.0
+        g = torch.Generator().manual_seed(100 + case)
+        idx = torch.randint(0, n, (q,), generator=g)
+        lat = (1.7 * bank[idx] + 0.3 * torch.randn(q, c, h, w, generator=g)).half()
+        v = (0.5 * torch.randn(q, c, h, w, generator=g)).half()
+        ns = {"math": math, "torch": torch, "latents": lat.clone(), "noise_pred": v.clone(),
+              "sigmas": torch.tensor(sig_list), "i": i, "num_inference_steps": steps,
+              "repellency_processor": proc, "latents_dtype": torch.float16}
+        torch.manual_seed(7 + case)
+        exec(compile(code, "safe_denoiser_pipeline.py:1141-1161", "exec"), ns)
+        torch.manual_seed(7 + case)
+        z = torch.randn_like(lat)                      # the draw the executed block made
+        key = f"flow/case{case}"
+        out[key + "/latents"] = lat.numpy()
+        out[key + "/v"] = v.numpy()
+        out[key + "/z"] = z.numpy()
+        out[key + "/sigma"] = np.float64(float(ns["sigma"]))
+        out[key + "/sigma_next"] = np.float64(float(ns["sigma_next"]))
+        out[key + "/x0_corrected"] = ns["latents_pred_0_repellenced"].float().numpy()
+        out[key + "/latents_next"] = ns["latents"].numpy()      # fp16
+
+
 def known_answers():
     """Scalars at the real SD-1.4 shape (SURVEY 8c recipe)."""
     g = torch.Generator().manual_seed(1234)
@@ -197,6 +239,12 @@ def known_answers():
 
 
 def main():
+    if "--flow-only" in sys.argv:           # added in round 2: leaves the other fixture files untouched
+        fx = {}
+        flow_step_cases(fx)
+        np.savez_compressed(os.path.join(HERE, "flow_cases.npz"), **fx)
+        print("flow_cases.npz written to", HERE)
+        return
     if "--batched-only" in sys.argv:        # added later: leaves the other fixture files untouched
         fx = {}
         batched_cases(fx)
@@ -220,6 +268,9 @@ def main():
     sparse_cases(fx)
     sparse_sdv3_cases(fx)
     np.savez_compressed(os.path.join(HERE, "sparse_cases.npz"), **fx)
+    fx = {}
+    flow_step_cases(fx)
+    np.savez_compressed(os.path.join(HERE, "flow_cases.npz"), **fx)
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(known_answers(), f, indent=1)
     print("golden fixtures written to", HERE)

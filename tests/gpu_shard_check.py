@@ -61,6 +61,21 @@ def main():
             if rank == 0:
                 print(f"Q={Q} N={N} world={world} {mode}: err x0 {err:.2e} denom {errd:.2e} gate {same_gate} "
                       f"median {ts[len(ts)//2]*1e3:.1f} us  {'OK' if good else 'FAIL'}", flush=True)
+    # SPELL baseline on an N-sharded bank: the force needs every row of the bank (partial sums + one all-reduce)
+    bank4 = orc.synthetic_bank(257, 4, 16, 16)
+    x4 = orc.synthetic_queries(bank4, 3, "near")
+    xr = x4.to(dev).clone()
+    term_f, wsum_f = Projector(NegativeBank(bank4.to(dev))).sparse(xr, 13.0, 1.6, want_term=True)
+    lo, hi = shard_bounds(257, rank, world)
+    xs = x4.to(dev).clone()
+    term_s, wsum_s = Projector(NegativeBank(bank4[lo:hi].to(dev)), group=dist.group.WORLD).sparse(xs, 13.0, 1.6, want_term=True)
+    torch.cuda.synchronize()
+    e1 = float((xs - xr).abs().max() / xr.abs().max())
+    e2 = float((wsum_s - wsum_f).abs().max() / wsum_f.abs().max().clamp_min(1e-30))
+    good = e1 <= 1e-5 and e2 <= 1e-5 and float(wsum_f.abs().max()) > 0
+    ok = ok and good
+    if rank == 0:
+        print(f"sparse (SPELL) world={world}: err x0 {e1:.2e} wsum {e2:.2e}  {'OK' if good else 'FAIL'}", flush=True)
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -104,6 +104,26 @@ def test_fused_flow_step_sd3(sigma_t, sigma_next):
     assert rel(out, want["next"]) <= TOL
 
 
+def test_fused_flow_step_against_reference_executed_golden():
+    """A8 pinned: the fused SD3 step vs the golden made by executing safe_denoiser_pipeline.py:1141-1161 (fp16 in/out)."""
+    import os
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "flow_cases.npz"))
+    bank4 = torch.from_numpy(d["flow/bank"])
+    proj = Projector(NegativeBank(bank4.cuda()))
+    for c in range(3):
+        k = f"flow/case{c}"
+        x, v, z = (torch.from_numpy(d[k + s]).cuda() for s in ("/latents", "/v", "/z"))      # fp16, as the pipeline holds them
+        sg, sn = float(d[k + "/sigma"]), float(d[k + "/sigma_next"])
+        x0c = torch.empty(x.shape, device="cuda")
+        out, _ = proj.flow_step(x.float(), v.float(), z.float(), sg, sn, 1.0, 0.03, 1e-8,
+                                normalize_channels=bank4.shape[1], x0c_out=x0c, out_dtype=torch.float16)
+        torch.cuda.synchronize()
+        assert out.dtype == torch.float16
+        assert rel(x0c, d[k + "/x0_corrected"]) <= 1.5e-3
+        assert rel(out.float(), d[k + "/latents_next"].astype(np.float32)) <= 1.5e-3
+
+
 def test_query_prepare_eps_to_x0_and_channel_norm():
     from safe_denoiser_b200 import _native as nv
     Q, C, HW = 3, 16, 64

@@ -458,6 +458,52 @@ def test_cfg4_sd3_full_size(nv):
     assert rel(got["weights"], want["weights"]) <= TOL
 
 
+def test_cfg5_full_size_against_oracle(nv):
+    """BASELINE config 5 at full size (Q = 128, N = 30000, 4x64x64, threshold semantics sigma = 3.15) against the
+    float64 closed form taken over row chunks: corrected x0 and denominators on all 128 rows, weights on 8 rows.
+    Covers the two-query-group kernels (UCfg<2>) with the chunked accumulate (more than 64 row blocks per chain),
+    dense and block-sparse, and the one-pass kernel (two passes of 64 rows)."""
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    N, Q = 30000, 128
+    bank4 = orc.synthetic_bank(N, 4, 64, 64)
+    x4 = orc.synthetic_queries(bank4[:4000], Q, "near")
+    rows = (0, 1, 31, 63, 64, 65, 100, 127)
+    want = orc.closed_form_chunked(x4.numpy(), bank4.numpy(), sigma=3.15, weight_rows=rows)
+    want_x0 = x4.numpy().reshape(Q, -1).astype(np.float64) - 0.33 * want["neg"]
+    bank = NegativeBank(bank4.cuda(), with_planes=True)
+    del bank4
+    for path, sparse in ((nv.PATH_AUTO, 0), (nv.PATH_AUTO, 1), (nv.PATH_FLASH, 0)):
+        nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, sparse)
+        x = x4.cuda().clone()
+        k = torch.empty(Q, N, device="cuda")
+        _, s = Projector(bank, path=path).correct(x, 3.15, 0.33, 1e-8, k_out=k)
+        torch.cuda.synchronize()
+        assert rel(x.reshape(Q, -1), want_x0) <= TOL, (path, sparse, "x0")
+        assert rel(s.denom, want["denom"]) <= TOL, (path, sparse, "denom")
+        w = (k[list(rows)] / s.denom[list(rows), None]).cpu().numpy()
+        assert rel(w, want["k"] / want["denom"][list(rows), None]) <= TOL, (path, sparse, "weights")
+    nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, 1)
+
+
+def test_split_accumulate_is_reproducible(nv):
+    """D = 2048 / 8192: phase B splits the bank rows over several CTAs per d-block; the split partials are summed in a
+    fixed order, so two runs on the same inputs give the same bits."""
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    for (c, h, w, n, q) in ((2, 32, 32, 1500, 16), (2, 64, 64, 900, 24)):
+        bank4 = orc.synthetic_bank(n, c, h, w)
+        x4 = orc.synthetic_queries(bank4, q, "near")
+        bank = NegativeBank(bank4.cuda(), with_planes=True)
+        outs = []
+        for _ in range(3):
+            s = Projector(bank, path=nv.PATH_UMMA).partial_sums(x4.cuda(), 3.15)
+            torch.cuda.synchronize()
+            outs.append((s.num.clone(), s.z.clone()))
+        want = orc.closed_form(x4.numpy(), bank4.numpy(), sigma=3.15)
+        assert rel(outs[0][0], want["num"]) <= TOL
+        for o in outs[1:]:
+            assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
+
+
 def test_cfg5_size_properties(nv):
     """BASELINE config 5 scale (Q = 128, N = 30000, threshold semantics) through size-independent properties:
     shard additivity (4 shards) and invariance of the negative mean under bank duplication."""

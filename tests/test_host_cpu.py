@@ -165,7 +165,10 @@ def test_epilogue_coefficients_match_scheduler_oracle():
         a, b = ep.ddpm_coefficients(ac, t), so.ddpm_coefficients(np.asarray(ac), t)
         for k in b:
             assert abs(a[k] - b[k]) <= 1e-12 * max(1.0, abs(b[k])), (t, k)
-    assert ep.ddpm_coefficients(ac, 1)["sqrt_ab_prev"] == 1.0        # t_prev < 0 -> abar_prev := 1
+    last = ep.ddpm_coefficients(ac, 1)
+    assert last["c_xt"] == 0.0                                       # DDPM, t_prev < 0 -> abar_prev := 1
+    assert abs(last["sqrt_ab_prev"] - ac[0] ** 0.5) < 1e-15          # DDIM: final_alpha_cumprod = alphas_cumprod[0]
+    assert ep.ddpm_coefficients(ac, 1, final_alpha_cumprod=1.0)["sqrt_ab_prev"] == 1.0     # set_alpha_to_one
 
 
 def test_lazy_scalar_behaves_like_a_float():

@@ -142,3 +142,33 @@ def test_known_answers_sd14_shape():
         want = ka[f"fast/{name}"]
         assert abs(np.abs(r["x_0_hat"] - x.numpy()).max() - want["max_abs_delta"]) < 1e-6
         assert abs(r["mean_x_0_hat"] - want["mean_x_0_hat"]) < 2e-3 * abs(want["mean_x_0_hat"]) + 1e-30
+
+
+def test_flow_step_oracle_against_reference_executed_lines():
+    """SURVEY A8 pin: flow_cases.npz was produced by EXECUTING models/sdv3/safe_denoiser_pipeline.py:1141-1161 (text
+    extracted by make_golden.py) around the reference's fast_sdv3 processor, fp16 latents and the cast back to fp16
+    included.  The float64 restatement must agree to fp16 rounding (the reference forms x0 = latents - sigma v in
+    fp16: eps 9.8e-4)."""
+    from oracle import scheduler_oracle as so
+    d = np.load(os.path.join(G, "flow_cases.npz"))
+    for c in range(3):
+        k = f"flow/case{c}"
+        x, v, z = (d[k + s].astype(np.float64) for s in ("/latents", "/v", "/z"))
+        sg, sn = float(d[k + "/sigma"]), float(d[k + "/sigma_next"])
+        ref = orc.closed_form(x - sg * v, d["flow/bank"], sigma=1.0, normalise_query=True)
+        w = so.flow_fused_step(x, v, ref["neg"].reshape(x.shape), 0.03, sg, sn, z)
+        want_x0c = d[k + "/x0_corrected"].astype(np.float64)
+        want_next = d[k + "/latents_next"].astype(np.float64)
+        assert d[k + "/latents_next"].dtype == np.float16
+        assert np.abs(w["x0_corrected"] - want_x0c).max() / np.abs(want_x0c).max() <= 1.5e-3
+        assert np.abs(w["next"] - want_next).max() / np.abs(want_next).max() <= 1.5e-3
+    assert float(d["flow/case2/sigma_next"]) == 0.0        # the last step: sigmas[i+1] does not exist
+
+
+def test_chunked_closed_form_equals_closed_form():
+    bank = orc.synthetic_bank(300, 4, 8, 8)
+    x = orc.synthetic_queries(bank, 5, "near")
+    a = orc.closed_form(x.numpy(), bank.numpy(), sigma=3.15)
+    b = orc.closed_form_chunked(x.numpy(), bank.numpy(), sigma=3.15, chunk=64, weight_rows=(0, 4))
+    assert np.allclose(a["Z"], b["Z"], rtol=1e-12) and np.allclose(a["num"], b["num"], rtol=1e-10, atol=1e-14)
+    assert np.allclose(a["k"][[0, 4]], b["k"], rtol=1e-12)
