@@ -298,6 +298,10 @@ def main():
     proj.correct(x, sigma, scale, eps, normalize_channels=normalize, gate_threshold=gate)
     launches_per_step = nv.launch_count() - c0
     barrier()
+    if world > 1:
+        # the ranks leave the host barrier some 100 us apart; a device-side rendezvous (one tiny all-reduce, enqueued
+        # and not waited for) lines the GPU timelines up, otherwise the first timed step measures that host skew
+        dist.all_reduce(torch.zeros(1, device=dev))
     for i in range(args.steps):
         x.copy_(x_src)
         flush_l2()
