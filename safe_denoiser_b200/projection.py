@@ -123,6 +123,15 @@ class ShardLink:
         dist.barrier(group)          # every rank's flag words are zero before the first merge
 
 
+def _nvtx(name):
+    """NVTX range around an entry point when SDN_NVTX=1 (nsys / ncu --nvtx timelines)."""
+    import contextlib
+    import os
+    if os.environ.get("SDN_NVTX", "0") != "1":
+        return contextlib.nullcontext()
+    return torch.cuda.nvtx.range(name)
+
+
 class _Scratch:
     __slots__ = ("num", "z", "xsq", "xq", "denom", "gate", "mean", "ws", "ws_bytes", "packed", "link")
 
@@ -255,6 +264,13 @@ class Projector:
                 bank_alpha: float = 1.0, k_out: torch.Tensor | None = None, want_num: bool = True):
         """conditioning(): x0 <- x0 - scale * neg in place.  Returns (neg or None, scratch); scratch
         holds denom [Q], gate [Q] (int32), mean [1] and num [Q,D] as device tensors."""
+        with _nvtx("sdn.correct"):
+            return self._correct(x0, sigma, scale, eps, normalize_channels=normalize_channels,
+                                 gate_threshold=gate_threshold, want_neg=want_neg, apply=apply, dist_power=dist_power,
+                                 bank_alpha=bank_alpha, k_out=k_out, want_num=want_num)
+
+    def _correct(self, x0, sigma, scale, eps, *, normalize_channels, gate_threshold, want_neg, apply, dist_power,
+                 bank_alpha, k_out, want_num):
         Q, xf = self._flat_query(x0)
         if (self.group is None and apply and normalize_channels == 0
                 and self.path in (nv.PATH_AUTO, nv.PATH_STREAM, nv.PATH_UMMA, nv.PATH_FLASH)
