@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg2-loop"],
+                    help="cfgN: one projection per step (BASELINE configs); cfg2-loop: the 50-step SD-1.4 sampler loop of "
+                         "configs[1] with a random-init stand-in UNet, the 11 in-window steps as ONE CUDA graph")
     ap.add_argument("--path", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 stream, 3 two-phase tcgen05, 4 tcgen05 reading only the bf16 hi plane, "
                          "5 one-pass tcgen05 (one HBM read of the bank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -195,9 +197,124 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def sampler_loop(args):
+    """BASELINE configs[1] as the sampler runs it (SURVEY f-4; ...threshold_time.py:514-576): 50 DDPM steps, B = 8 with
+    CFG (16 rows), N = 515; in the window t in [780, 1000] (11 steps) every step is  UNet -> eps->x0 -> projection ->
+    gate -> re-noise -> scheduler step  through Projector.ddpm_step (device-side gate, no .item()), and the 11 steps
+    are captured in ONE CUDA graph.  diffusers is absent offline, so the UNet is a random-init stand-in of three
+    convolutions in stock torch and the out-of-window steps are the plain DDPM update in torch."""
+    import torch
+    from safe_denoiser_b200 import _native as nv
+    from safe_denoiser_b200.epilogue import ddpm_coefficients, ddpm_timesteps, sd14_alphas_cumprod
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    from oracle import repellency_oracle as orc
+    nv.lib()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    Q, N, C, H, W = 16, 515, 4, 64, 64
+    sigma, scale, eps, thr = 3.15, 0.33, 1e-8, 4.54
+    bank_cpu = orc.synthetic_bank(N, C, H, W)
+    bank = NegativeBank(bank_cpu.to(dev), with_planes=True)
+    proj = Projector(bank)
+    torch.manual_seed(0)
+    unet = torch.nn.Sequential(torch.nn.Conv2d(C, 64, 3, padding=1), torch.nn.SiLU(), torch.nn.Conv2d(64, 64, 3, padding=1),
+                               torch.nn.SiLU(), torch.nn.Conv2d(64, C, 3, padding=1)).to(dev).eval()
+    ac = sd14_alphas_cumprod()
+    ts = ddpm_timesteps(50)
+    window = [t for t in ts if 780 <= t <= 1000]
+    rest = [t for t in ts if t < 780]
+    co = {t: ddpm_coefficients(ac, t) for t in ts}
+    g = torch.Generator(device=dev).manual_seed(1)
+    x_init = torch.randn(Q, C, H, W, device=dev, generator=g)
+    noise = torch.randn(len(ts), 2, Q, C, H, W, device=dev, generator=g)
+    x = x_init.clone()
+
+    def in_window(with_projection=True):
+        nonlocal x
+        for i, t in enumerate(window):
+            with torch.no_grad():
+                e = unet(x)
+            if with_projection:
+                x, _ = proj.ddpm_step(x, e, noise[i, 0], noise[i, 1], co[t], sigma, scale, eps, gate_threshold=thr)
+            else:
+                x = x + 0.0 * e
+
+    def out_of_window():
+        nonlocal x
+        for i, t in enumerate(rest):
+            c = co[t]
+            with torch.no_grad():
+                e = unet(x)
+                x0 = (x - c["sqrt_1m_ab"] * e) / c["sqrt_ab"]
+                x = c["c_x0"] * x0 + c["c_xt"] * x + c["sigma_noise"] * noise[len(window) + i, 0]
+
+    def graph_of(fn):
+        nonlocal x
+        x = x_init.clone()
+        fn()                                   # eager warm-up: scratch, kernel attributes, planes
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        x = x_init.clone()
+        xin = x
+        with torch.cuda.graph(gr):
+            fn()
+        return gr, xin, x
+
+    c0 = nv.launch_count()
+    x = x_init.clone()
+    in_window()
+    launches_window = nv.launch_count() - c0
+    g_win, win_in, win_out = graph_of(in_window)
+    g_unet, _, _ = graph_of(lambda: in_window(False))
+    g_rest, rest_in, rest_out = graph_of(out_of_window)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    reps = max(3, args.steps // 10)
+
+    def full_loop():
+        win_in.copy_(x_init)
+        g_win.replay()
+        rest_in.copy_(win_out)
+        g_rest.replay()
+
+    t_win = timed(g_win.replay, reps)
+    t_unet = timed(g_unet.replay, reps)
+    t_loop = timed(full_loop, reps)
+    finite = bool(torch.isfinite(rest_out).all().item())
+    proj_ms = (t_win - t_unet) / len(window)
+    line = {"metric": "repellency projections/sec", "unit": "projections/s", "n_gpus": 1, "steps": reps, "warmup": 1,
+            "value": Q * len(window) / (max(t_win - t_unet, 1e-9) * 1e-3), "ms_per_step": proj_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gpu_launches": int(launches_window * reps),
+            "config": {"workload": "SD-1.4 nudity sampling loop: B=8 with CFG (16 rows), N=515, 50 DDPM steps, random-init "
+                                   "stand-in UNet (3 convolutions; diffusers is absent offline) -- BASELINE configs[1]",
+                       "Q": Q, "N": N, "latent": [C, H, W], "in_window_steps": len(window), "window": "t in [780, 1000]",
+                       "graph": "the 11 in-window steps (UNet + Projector.ddpm_step each, device-side gate, no host sync) are ONE CUDA graph; "
+                                "the 39 plain DDPM steps a second one"},
+            "loop": {"ms_50_steps": t_loop, "in_window_graph_ms": t_win, "same_graph_without_projection_ms": t_unet,
+                     "projection_and_fused_step_ms_per_in_window_step": proj_ms,
+                     "projection_share_of_in_window_step": (t_win - t_unet) / t_win,
+                     "projection_share_of_the_50_step_loop": (t_win - t_unet) / t_loop,
+                     "kernels_per_in_window_step": launches_window / len(window), "latents_finite": finite},
+            "e2e": None, "roofline": None, "cpu_baseline": None}
+    emit(line)
+
+
 def main():
     args = parse()
     _quiet_stdout()
+    if args.workload == "cfg2-loop":
+        return sampler_loop(args)
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -104,6 +104,38 @@ def test_fused_flow_step_sd3(sigma_t, sigma_next):
     assert rel(out, want["next"]) <= TOL
 
 
+def test_in_window_steps_replay_from_one_cuda_graph():
+    """SURVEY f-4: several consecutive in-window SD-1.4 steps (device-side gate, no host sync) captured in ONE CUDA
+    graph give the same latents as the same steps launched eagerly."""
+    from safe_denoiser_b200.epilogue import ddpm_coefficients, ddpm_timesteps, sd14_alphas_cumprod
+    Q = 16
+    bank4, proj, g, shape, idx, ac = _setup(Q, N=200, C=4, H=64, W=64, seed=4)
+    acp = sd14_alphas_cumprod()
+    steps = [t for t in ddpm_timesteps(50) if t >= 900]            # 981, 961, 941, 921, 901
+    cos = [ddpm_coefficients(acp, t) for t in steps]
+    noise = torch.randn((len(steps), 3) + shape, generator=g).cuda()
+    x_init = (cos[0]["sqrt_ab"] * bank4[idx] + cos[0]["sqrt_1m_ab"] * torch.randn(shape, generator=g)).cuda()
+
+    def run(x):
+        for i, co in enumerate(cos):
+            eps_pred = 0.1 * x + noise[i, 0]                        # stand-in for the UNet
+            x, s = proj.ddpm_step(x, eps_pred, noise[i, 1], noise[i, 2], co, 3.15, 0.33, 1e-8, gate_threshold=2.0)
+        return x
+
+    want = run(x_init.clone())
+    torch.cuda.synchronize()
+    xin = x_init.clone()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        out = run(xin)
+    for _ in range(2):
+        xin.copy_(x_init)
+        gr.replay()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert torch.equal(out, want)
+
+
 def test_fused_flow_step_against_reference_executed_golden():
     """A8 pinned: the fused SD3 step vs the golden made by executing safe_denoiser_pipeline.py:1141-1161 (fp16 in/out)."""
     import os
