@@ -8,31 +8,35 @@
 //   grid     D / 128 CTAs, one per SM (co-resident: they exchange data while running).  Four consecutive CTAs form a
 //            group that covers a 512-wide "super-slice" of D; the query rows of a pass are stacked as 64 hi parts +
 //            64 lo parts = the 128 lanes of tensor memory.
-//   phase A  (distances) CTA r of a group takes the tiles t = r (mod 4) over the WHOLE super-slice, in four chunks of
-//            128 d (one 32 KiB stage each: hi and lo planes of [64 rows][128 d], TMA, L2 evict_last):
-//            S[q][i] = sum_{d in super-slice} X[q][d] bank[i][d], tcgen05.mma with A = X[:, super-slice] (bf16 hi/lo,
-//            resident in TENSOR MEMORY for the whole kernel), B = the chunk (K-major).  The group's 4:1 reduction over
-//            d thus happens inside the tensor core.  (Built and measured before: a DSMEM exchange between the four
-//            CTAs, 1.9 us per tile in mbarrier round trips; and 16 rows x 512 d per CTA and tile, 3.2 us per tile
-//            because a tcgen05.mma with N = 16 costs as much as one with N = 64 -- the A operand bounds it.)
-//            The accumulator is drained every two chunks (32 MMAs): the tensor core adds with truncation.
+//   phase A  (distances) CTA r of a group takes the 128-row tiles t = r (mod 4) over the WHOLE super-slice, in eight
+//            chunks of 64 d (one 32 KiB stage each: hi and lo planes of [128 rows][64 d], TMA, L2 evict_last):
+//            S[q][i] = sum_{d in super-slice} X[q][d] bank[i][d], tcgen05.mma M128 x N128 x K16 with A = X[:, super-
+//            slice] (bf16 hi/lo, resident in TENSOR MEMORY for the whole kernel), B = the chunk (K-major).  The
+//            group's 4:1 reduction over d thus happens inside the tensor core.  Round-2 measurements that shaped this:
+//            an MMA whose A operand comes from tensor memory costs >= 64 clk whatever N is (A-read bound), so 64-row
+//            tiles (N = 64) made phase A alone tensor-bound at 80 us for cfg3 (56 us with 1/16 of the MMAs);
+//            N = 128 halves the MMA count per byte.  The accumulator is drained every four chunks (32 MMAs): the
+//            tensor core adds with truncation.
 //   exchange S[q][i] = sum over the D/512 groups.  The group partials go through L2 as self-validating 16-byte lines
 //            {v, tag, v, tag} (no fence, no flag) to work units of 4 rows x 32 queries dealt round-robin over ALL
-//            4 x #CTAs warps of the level-2 role: a unit sums the groups in order, computes k = exp(-dist / 2 sigma^2)
-//            and publishes the weights as fp32 words whose low 4 mantissa bits carry the tile's round number (again no
-//            fence, no flag: every word validates itself).
-//   phase B  (accumulate) CTA j owns the d-slice [128 j, 128 j + 128): num[q][slice] += sum_i k[q][i] bank[i][slice],
-//            tcgen05.mma with A = the weights (bf16 hi/lo written to TMEM by tcgen05.st), B = the tile [64 rows][128 d]
-//            viewed MN-major, loaded AGAIN by TMA (evict_first) when the tile's weights show up: a hit in the 126 MB L2
-//            because phase A never runs more than `window` tiles ahead.  The accumulator stays in tensor memory for
-//            the whole kernel; the epilogue applies the correction of conditioning() when fused.
+//            4 x #CTAs warps of the level-2 role: a unit sums the groups in order, computes k = exp(-dist / 2 sigma^2),
+//            writes the weights as bf16 hi | lo into the tile's slot of a global ring in the layout phase B wants as
+//            an MMA operand, writes its z partial, and then releases the slot: fence + one add on the tile's counter.
+//   phase B  (accumulate) CTA j owns the d-slice [128 j, 128 j + 128): num[slice][q] += sum_i bank[i][slice] k[q][i],
+//            tcgen05.mma with A = the tile [64 rows][128 d] viewed MN-major, loaded AGAIN by TMA (evict_first) -- a
+//            hit in the 126 MB L2 because phase A never runs more than `window` tiles ahead -- and B = the weights
+//            [64 rows][hi 64 | lo 64], loaded by TMA from the ring once the tile's counter says all 64 units are
+//            done.  Nothing of phase B passes through registers (the first version converted the weights in every CTA
+//            and stored them to tensor memory: a serial 1.9 us per 64 rows and CTA, the limiter of that version).
+//            The accumulator stays in tensor memory for the whole kernel; the epilogue applies the correction of
+//            conditioning() when fused.
 //
-// Every sum has a fixed order (group index, row index): results are bit-reproducible run to run.
+// Every sum has a fixed order (group index, row index, unit index): results are bit-reproducible run to run.
 //
-// Warp roles (16 warps): 0 TMA producer phase A | 1 MMA issuer (event loop over "tile ta loaded" / "weights and tile
-// tb ready") | 4-7 query prologue, then phase-A drain: TMEM -> registers -> LL lines | 8-11 weights: global -> bf16
-// hi/lo -> TMEM (warp 8 also issues the second TMA read of the tile), z_q, and the final epilogue | 12-15 level-2 work
-// units: ||x||^2, sum over groups, exp, publish.
+// Warp roles (16 warps): 0 TMA producer phase A | 1 MMA issuer (event loop over "chunk loaded" / "weights and half
+// tile loaded") | 2 phase-B producer: polls the tile counters, issues the TMA loads of weights + second read |
+// 4-7 query prologue (chunks 0-1), then phase-A drain: TMEM -> registers -> LL lines | 8-11 query prologue (chunks
+// 2-3), then z_q from the units' partials, then the final epilogue | 12-15 level-2 work units.
 #include <cuda.h>
 
 #include <algorithm>
@@ -46,37 +50,48 @@
 
 namespace sdn {
 
-constexpr int kFR = 64;                 // bank rows per tile
+constexpr int kFR = 128;                // bank rows per tile (N of the phase-A MMA)
+constexpr int kFHB = 64;                // bank rows per phase-B stage (K of its MMAs: 4 steps of 16)
 constexpr int kFDS = 128;               // d per CTA in phase B
 constexpr int kFGS = 4;                 // CTAs per group
 constexpr int kFSuper = kFDS * kFGS;    // d per group in phase A (512)
+constexpr int kFChunkD = 64;            // d per phase-A stage
+constexpr int kFChunks = kFSuper / kFChunkD;   // 8 chunks per own tile
 constexpr int kFQ = 64;                 // query rows per pass
 constexpr int kFJobRows = 4;            // rows of a tile per level-2 job
-constexpr int kFJobs = kFR / kFJobRows; // 16 jobs per tile, two work units (halves of the query rows) each
-constexpr int kFRing = 32;              // slots of the global exchange rings: phase A runs at most kFWindow < kFRing tiles ahead of phase B
-constexpr int kFWindow = 12;            // tiles between the two reads of the bank: 12 x 4 MiB stay in the 126 MB L2 (and < the 16 tiles between two units of a level-2 worker)
+constexpr int kFJobs = kFR / kFJobRows; // 32 jobs per tile, two work units (halves of the query rows) each
+constexpr int kFUnits = kFJobs * 2;     // counter increments per tile
+constexpr int kFRingL = 16;             // slots of the level-1 partial ring (2 MiB each)
+constexpr int kFRingP = 32;             // slots of the weight / z-partial / counter rings
+constexpr int kFWindow = 8;             // tiles between the two reads of the bank: 8 x 8 MiB stay in the 126 MB L2 (6: 132 us, 8: 116 us, 12: 114 us at cfg3); also what
+                                        // makes ring reuse safe (2 window + 6 <= kFRingP, window <= kFRingL, window < 8 tiles
+                                        // between two units of a level-2 worker)
 constexpr int kFThreads = 512;
 constexpr int kFMaxCtas = 128;
 constexpr int kFMaxGroups = kFMaxCtas / kFGS;
-constexpr uint32_t kFStageBytes = 32768;   // hi + lo planes of [64 rows][128 d] bf16 (phase A: one chunk of the super-slice; phase B: the CTA's slice)
-constexpr int kFSA = 3;                 // stages of phase A (HBM stream)
-constexpr int kFSB = 3;                 // stages of phase B (second read: L2)
+constexpr uint32_t kFStageA = 32768;    // hi + lo planes of [128 rows][64 d] bf16
+constexpr uint32_t kFStageB = 49152;    // weights [64 rows][128] bf16 (16 KiB) + hi + lo planes of [64 rows][128 d]
+constexpr uint32_t kFStageRegion = 224 * 1024;
+constexpr int kFMaxStages = 4;
 constexpr uint32_t kFTmemCols = 512;
 constexpr uint32_t kFColX = 0;          // X operand [128 stacked rows][512 d] bf16: 256 columns
-constexpr uint32_t kFColS = 256;        // S accumulator [128][64 bank rows]
-constexpr uint32_t kFColP = 320;        // weight operands: 2 x 32 columns
-constexpr uint32_t kFColAcc = 384;      // num accumulator [128][128 d]
+constexpr uint32_t kFColS = 256;        // S accumulator [128][128 bank rows]
+constexpr uint32_t kFColAcc = 384;      // num accumulator [128 d][64 hi-part columns | 64 lo-part columns]
 constexpr uint32_t kFSpinLimit = 1u << 24;
-constexpr int kFPitch = 132;            // floats per staged row (thread = row accesses are conflict-free per quarter warp)
-constexpr uint32_t kFSmemBytes = (kFSA + kFSB) * kFStageBytes + 1024 /*align*/ + 1536 /*barriers, xsq*/;
+constexpr int kFPitch = 132;            // floats per staged query row (thread = row accesses are conflict-free per quarter warp)
+constexpr uint32_t kFXStageBytes = 4u * kFQ * kFPitch * 4u;   // four chunks of [64 rows][128 d] staged at start-up
+constexpr uint32_t kFXStageOff = kFStageRegion - kFXStageBytes;
+constexpr uint32_t kFSmemBytes = kFStageRegion + 1024 /*align*/ + 2048 /*barriers, xsq, z*/;
 
-// Arena: library-owned per-device synchronisation memory of the one-pass kernel (zeroed once; tags grow
-// monotonically over launches, so stale lines never match).
+// Arena: library-owned per-device synchronisation memory of the one-pass kernel (zeroed once; tags and counters grow
+// monotonically over launches, so stale data never matches).
 struct FlashArena {
   uint32_t* epoch;      // [0] sequence number of the next launch's tile 0, [1] launch counter
   uint8_t* xsq_ll;      // [kFMaxCtas][128] 16-byte lines: ||x_q||^2 partial of every CTA
-  uint8_t* part_ll;     // [ring][group 32][job 16][q 64][2 lines]   level-2 fan-in
-  float* gw;            // [ring][job 16][q 64][4 rows]  published weights
+  uint8_t* part_ll;     // [kFRingL][group 32][job 32][q 64][2 lines]   level-2 fan-in
+  __nv_bfloat16* gp;    // [kFRingP][128 rows][hi 64 | lo 64]   published weights (phase-B MMA operand)
+  float* gz;            // [kFRingP][job 32][q 64]   z partials of the units
+  uint32_t* counter;    // [kFRingP]   units done, 64 per tile and round
   uint32_t* diag;       // host-mapped: written before a timeout trap
   unsigned long long* trace;   // SDN_FLASH_TRACE=1: [cta][tile < 64][16 events] globaltimer ns (null otherwise)
 };
@@ -84,9 +99,9 @@ struct FlashArena {
 struct FlashArgs {
   const float* xq;      // [Q][D] query the distances are taken on
   const float* sqnorm;  // [N]
-  int Q, N, ntiles, ngroups, window;
-  unsigned mma_sleep, poll_sleep;     // back-off of the polling loops (ns)
-  unsigned dbg;                        // SDN_FLASH_DBG experiments: 1 = one phase-A MMA per chunk, 2 = one phase-B MMA per tile (wrong results)
+  int Q, N, ntiles, nhb, ngroups, window, nsa, nsb;
+  unsigned poll_sleep;                // back-off of the polling loops (ns)
+  unsigned dbg;                       // SDN_FLASH_DBG experiments (wrong results): 1 = one phase-A MMA per chunk, 2 = one phase-B MMA per stage
   int64_t D;
   float inv2s2, alpha; int power;
   float* num_out;       // [Q][D] or null
@@ -116,10 +131,6 @@ __device__ __forceinline__ void f_trace(const FlashArgs& a, int tile, int ev) {
   }
 }
 
-__device__ __forceinline__ void f_trace_val(const FlashArgs& a, int tile, int ev, unsigned long long v) {
-  if (a.ar.trace && tile < kFTraceTiles) a.ar.trace[((size_t)blockIdx.x * kFTraceTiles + tile) * kFTraceEvents + ev] = v;
-}
-
 // bounded mbarrier wait (a broken pipeline must not hang the GPU)
 __device__ __forceinline__ void f_wait(const FlashArgs& a, uint64_t* bar, uint32_t parity, uint32_t code, uint32_t tile) {
   uint32_t done = 0;
@@ -127,19 +138,6 @@ __device__ __forceinline__ void f_wait(const FlashArgs& a, uint64_t* bar, uint32
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(u_smem(bar)), "r"(parity) : "memory");
-    if (spin > kFSpinLimit) f_timeout(a, code, tile, parity);
-  }
-}
-
-// same, observing arrivals made by peer CTAs of the cluster
-__device__ __forceinline__ void f_wait_cluster(const FlashArgs& a, uint64_t* bar, uint32_t parity, uint32_t code, uint32_t tile) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(u_smem(bar)), "r"(parity) : "memory");
     if (spin > kFSpinLimit) f_timeout(a, code, tile, parity);
@@ -160,44 +158,56 @@ __device__ __forceinline__ void f_tma_2d_hint(void* dst, const CUtensorMap* map,
       ::"r"(u_smem(dst)), "l"(map), "r"(u_smem(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 
+__device__ __forceinline__ void f_st_release_cta(int* p, int v) {
+  asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(u_smem(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int f_ld_acquire_cta(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(u_smem(p)) : "memory");
+  return v;
+}
+
 struct FSmem {
-  uint8_t* stages;      // [kFSA phase-A stages | kFSB phase-B stages] x 32 KiB
-  uint64_t* afull; uint64_t* aempty;      // [kFSA]
-  uint64_t* bfull; uint64_t* bempty;      // [kFSB]
-  uint64_t* sfull; uint64_t* sempty;      // [1] S accumulator (one drain per two chunks)
-  uint64_t* pfull; uint64_t* pempty;      // [2] weight operands
+  uint8_t* stages;      // [nsa phase-A stages x 32 KiB | nsb phase-B stages x 48 KiB]
+  uint64_t* afull; uint64_t* aempty;      // [kFMaxStages]
+  uint64_t* bfull; uint64_t* bempty;      // [kFMaxStages]
+  uint64_t* sfull; uint64_t* sempty;      // [1] S accumulator (one drain per four chunks)
   uint64_t* xfull; uint64_t* accfull;     // [1]
-  uint64_t* xload;                        // [4 warps][2] query rows of one prologue warp staged in shared memory
+  uint64_t* xload;                        // [8 warps][2 chunks] query rows of one prologue warp staged in shared memory
   uint32_t* tmem_base;
+  int* pub_upto;        // tiles < this have all their weights published (phase-B producer -> z warps)
+  int* zdone;           // tiles < this have their z partials summed (z warps -> MMA issuer: ring reuse)
   float* xsq;           // [64]
-  float* xsq_half;      // [128]  (||x||^2 halves at start, z_q at the end)
+  float* xsq_half;      // [128]  (||x||^2 halves at start, z_q halves at the end)
+  float* zq;            // [64]
 };
 
 __device__ __forceinline__ FSmem f_carve(unsigned char* raw) {
   FSmem s;
   const uintptr_t a = (reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023;
   s.stages = reinterpret_cast<uint8_t*>(a);
-  uint64_t* b = reinterpret_cast<uint64_t*>(s.stages + (size_t)(kFSA + kFSB) * kFStageBytes);
-  s.afull = b; b += 4;
-  s.aempty = b; b += 4;
-  s.bfull = b; b += 4;
-  s.bempty = b; b += 4;
-  s.sfull = b; b += 4;
-  s.sempty = b; b += 4;
-  s.pfull = b; b += 2;
-  s.pempty = b; b += 2;
+  uint64_t* b = reinterpret_cast<uint64_t*>(s.stages + kFStageRegion);
+  s.afull = b; b += kFMaxStages;
+  s.aempty = b; b += kFMaxStages;
+  s.bfull = b; b += kFMaxStages;
+  s.bempty = b; b += kFMaxStages;
+  s.sfull = b; b += 1;
+  s.sempty = b; b += 1;
   s.xfull = b; b += 1;
   s.accfull = b; b += 1;
-  s.xload = b; b += 8;
+  s.xload = b; b += 16;
   s.tmem_base = reinterpret_cast<uint32_t*>(b); b += 1;
-  s.xsq = reinterpret_cast<float*>(b);          // 39 x 8 = 312 bytes of barriers so far
-  s.xsq_half = s.xsq + 128;
+  s.pub_upto = reinterpret_cast<int*>(b); b += 1;
+  s.zdone = reinterpret_cast<int*>(b); b += 1;     // 39 x 8 = 312 bytes so far
+  s.xsq = reinterpret_cast<float*>(b);
+  s.xsq_half = s.xsq + 64;
+  s.zq = s.xsq_half + 128;                        // + 256 floats = 1336 bytes
   return s;
 }
 
 __global__ void __launch_bounds__(kFThreads, 1)
 k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-        const __grid_constant__ FlashArgs a) {
+        const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ FlashArgs a) {
   extern __shared__ unsigned char smem_raw[];
   const FSmem sm = f_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,22 +215,26 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
   const int grp = cta / kFGS, rk = cta % kFGS;
   const int d0 = cta * kFDS;            // phase-B slice
   const int ds0 = grp * kFSuper;        // phase-A super-slice
-  const int ntiles = a.ntiles;
+  const int ntiles = a.ntiles, nhb = a.nhb;
+  const int nsa = a.nsa, nsb = a.nsb;
   const int ngroups = a.ngroups;
-  // query staging (two buffers of [64 rows][132 floats]) lives in the phase-B stages, which are idle until the first
-  // weights arrive; the epilogue staging in the phase-A stages, which are idle by then
-  float* const xstage = reinterpret_cast<float*>(sm.stages + (size_t)kFSA * kFStageBytes);
-  float* const estage = reinterpret_cast<float*>(sm.stages);
+  uint8_t* const bstages = sm.stages + (size_t)nsa * kFStageA;
+  // query staging (four buffers of [64 rows][132 floats]) lives at the end of the stage region until the prologue is
+  // done: the stages that overlap it take their first load after `xfull`
+  float* const xstage = reinterpret_cast<float*>(sm.stages + kFXStageOff);
+  const int first_gated_a = (int)(kFXStageOff / kFStageA);   // phase-A stages >= this overlap the staging area
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFSA; ++s) { u_mbar_init(&sm.afull[s], 1); u_mbar_init(&sm.aempty[s], 1); }
-    for (int s = 0; s < kFSB; ++s) { u_mbar_init(&sm.bfull[s], 1); u_mbar_init(&sm.bempty[s], 1); }
+    for (int s = 0; s < kFMaxStages; ++s) {
+      u_mbar_init(&sm.afull[s], 1); u_mbar_init(&sm.aempty[s], 1);
+      u_mbar_init(&sm.bfull[s], 1); u_mbar_init(&sm.bempty[s], 1);
+    }
     u_mbar_init(sm.sfull, 1); u_mbar_init(sm.sempty, 4);
-    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.pfull[b], 4); u_mbar_init(&sm.pempty[b], 1); }
-    u_mbar_init(sm.xfull, 4); u_mbar_init(sm.accfull, 1);
-    for (int w = 0; w < 8; ++w) u_mbar_init(&sm.xload[w], 1);
+    u_mbar_init(sm.xfull, 8); u_mbar_init(sm.accfull, 1);
+    for (int w = 0; w < 16; ++w) u_mbar_init(&sm.xload[w], 1);
+    *sm.pub_upto = 0; *sm.zdone = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
+    u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo); u_prefetch_map(&tm_p);
     if (cta == 0 && a.epi.zero_mean && a.epi.mean_out) { *a.epi.mean_out = 0.f; __threadfence(); }
   }
   if (warp == 1) u_tmem_alloc(sm.tmem_base, kFTmemCols);
@@ -235,133 +249,182 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
   uint64_t pol_keep, pol_drop;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
-  // a stage: hi and lo planes of [64 rows][128 d], two boxes of [64 rows][64 d] per plane (8 KiB each)
-  auto load_tile = [&](uint8_t* st, uint64_t* bar, int t, int dd, uint64_t policy) {
-    u_mbar_expect_tx(bar, kFStageBytes);
-    const int r0 = t * kFR;
-    f_tma_2d_hint(st, &tm_hi, dd, r0, bar, policy);
-    f_tma_2d_hint(st + 8192, &tm_hi, dd + 64, r0, bar, policy);
-    f_tma_2d_hint(st + 16384, &tm_lo, dd, r0, bar, policy);
-    f_tma_2d_hint(st + 24576, &tm_lo, dd + 64, r0, bar, policy);
-  };
-  // phase A unit ua = (own tile i, chunk c): tile t = rk + 4 i, d in [ds0 + 128 c, +128)
+  // phase A unit ua = (own tile i, chunk c): tile t = rk + 4 i, d in [ds0 + 64 c, +64)
   const int nown = (ntiles - rk + kFGS - 1) / kFGS;
-  const int nua = nown * kFGS;
-  auto load_a = [&](int ua) {
-    const int t = rk + kFGS * (ua >> 2), c = ua & 3;
-    if (c == 0) f_trace(a, t, 0);
-    load_tile(sm.stages + (size_t)(ua % kFSA) * kFStageBytes, &sm.afull[ua % kFSA], t, ds0 + c * kFDS, pol_keep);
-  };
-  auto load_b = [&](int t) {
-    load_tile(sm.stages + (size_t)(kFSA + t % kFSB) * kFStageBytes, &sm.bfull[t % kFSB], t, d0, pol_drop);
-  };
+  const int nua = nown * kFChunks;
 
   if (warp == 0) {
     // ============================================================ TMA producer, phase A (HBM stream)
     if (lane == 0) {
       for (int ua = 0; ua < nua; ++ua) {
-        if (ua >= kFSA) f_wait(a, &sm.aempty[ua % kFSA], (uint32_t)(((ua / kFSA) + 1) & 1), 0x100, ua);
-        load_a(ua);
+        const int s = ua % nsa;
+        if (ua >= nsa) f_wait(a, &sm.aempty[s], (uint32_t)(((ua / nsa) + 1) & 1), 0x100, ua);
+        else if (s >= first_gated_a) f_wait(a, sm.xfull, 0, 0x101, ua);     // this stage doubles as query staging
+        const int t = rk + kFGS * (ua / kFChunks), c = ua % kFChunks;
+        if (c == 0) f_trace(a, t, 0);
+        if (c == 4) f_trace(a, t, 14);
+        if (c == 7) f_trace(a, t, 15);
+        uint8_t* st = sm.stages + (size_t)s * kFStageA;
+        const int r0 = t * kFR, dd = ds0 + c * kFChunkD;
+        // a stage: hi and lo planes of [128 rows][64 d], two boxes of [64 rows][64 d] per plane (8 KiB each); a box
+        // entirely past the last bank row is skipped (its S columns are never used)
+        const bool two = r0 + 64 < a.N;
+        u_mbar_expect_tx(&sm.afull[s], two ? kFStageA : kFStageA / 2);
+        f_tma_2d_hint(st, &tm_hi, dd, r0, &sm.afull[s], pol_keep);
+        f_tma_2d_hint(st + 16384, &tm_lo, dd, r0, &sm.afull[s], pol_keep);
+        if (two) {
+          f_tma_2d_hint(st + 8192, &tm_hi, dd, r0 + 64, &sm.afull[s], pol_keep);
+          f_tma_2d_hint(st + 24576, &tm_lo, dd, r0 + 64, &sm.afull[s], pol_keep);
+        }
       }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idA = u_idesc(128, kFR, 0, 0);      // S[128][64 rows]   = X (TMEM) x chunk (K-major)
-      constexpr uint32_t idB = u_idesc(128, kFDS, 0, 1);     // num[128][128 d] += P (TMEM) x tile (MN-major)
+      constexpr uint32_t idA = u_idesc(128, kFR, 0, 0);       // S[128 stacked q][128 rows] = X (TMEM) x chunk (K-major)
+      constexpr uint32_t idBf = u_idesc(kFDS, 128, 1, 1);     // num[128 d][hi | lo] += bank_hi^T x [P_hi | P_lo]
+      constexpr uint32_t idBh = u_idesc(kFDS, 64, 1, 1);      // num[128 d][hi]      += bank_lo^T x P_hi
       f_wait(a, sm.xfull, 0, 0x200, 0);
       u_fence_after();
-      int ua = 0, tb = 0;                 // next phase-A unit (own tile, chunk) / next phase-B tile
+      int ua = 0, hb = 0;                 // next phase-A unit (own tile, chunk) / next phase-B half tile
       uint32_t idle = 0;
-      while (tb < ntiles) {
+      while (hb < nhb || ua < nua) {
         bool did = false;
-        if (u_mbar_test(&sm.pfull[tb & 1], (uint32_t)((tb >> 1) & 1)) &&
-            u_mbar_test(&sm.bfull[tb % kFSB], (uint32_t)((tb / kFSB) & 1))) {
-          // ---- phase B of tile tb: 4 K steps of 16 bank rows
+        if (hb < nhb && u_mbar_test(&sm.bfull[hb % nsb], (uint32_t)((hb / nsb) & 1))) {
+          // ---- phase B of half tile hb: 4 K steps of 16 bank rows
           u_fence_after();
-          f_trace(a, tb, 8);
-          const uint32_t base = u_smem(sm.stages + (size_t)(kFSA + tb % kFSB) * kFStageBytes);
+          f_trace(a, hb >> 1, (hb & 1) ? 13 : 8);
+          const uint32_t base = u_smem(bstages + (size_t)(hb % nsb) * kFStageB);
           const uint32_t acc = tmem + kFColAcc;
-          const uint32_t pb = tmem + kFColP + (uint32_t)(tb & 1) * 32;
 #pragma unroll
-          for (int kk = 0; kk < kFR / 16; ++kk) {
+          for (int kk = 0; kk < kFHB / 16; ++kk) {
             if ((a.dbg & 2) && kk > 0) break;
-            const uint64_t bh = u_desc(base + kk * 2048, 8192, 1024);
-            const uint64_t bl = u_desc(base + 16384 + kk * 2048, 8192, 1024);
-            u_mma_ts(acc, pb + kk * 8, bh, idB, (tb > 0 || kk > 0) ? 1u : 0u);
-            u_mma_ts(acc, pb + kk * 8, bl, idB, 1u);
+            const uint64_t pw = u_desc(base + kk * 2048, 8192, 1024);               // P^T, MN-major: hi box | lo box
+            const uint64_t ah = u_desc(base + 16384 + kk * 2048, 8192, 1024);       // bank^T, MN-major
+            const uint64_t al = u_desc(base + 32768 + kk * 2048, 8192, 1024);
+            u_mma(acc, ah, pw, idBf, (hb > 0 || kk > 0) ? 1u : 0u);
+            u_mma(acc, al, pw, idBh, 1u);
           }
-          u_commit(&sm.bempty[tb % kFSB]);
-          u_commit(&sm.pempty[tb & 1]);
-          if (tb == ntiles - 1) u_commit(sm.accfull);
-          ++tb;
+          u_commit(&sm.bempty[hb % nsb]);
+          ++hb;
+          if (hb == nhb) u_commit(sm.accfull);
           did = true;
         }
-        // phase A stays within `window` tiles of phase B: the exchange rings (kFRing slots) are reused safely and the
-        // tiles waiting for their second read fit in the L2.  The S accumulator is drained every two chunks (half h).
+        // phase A stays within `window` tiles of phase B (and of the z warps): the exchange rings are reused safely and
+        // the tiles waiting for their second read fit in the L2.  The S accumulator is drained every four chunks.
         if (ua < nua) {
-          const int ta = rk + kFGS * (ua >> 2), c = ua & 3;
-          const int sh = ua >> 1;           // drains so far = halves started
-          if (ta - tb < a.window && u_mbar_test(&sm.afull[ua % kFSA], (uint32_t)((ua / kFSA) & 1)) &&
-              ((c & 1) || sh == 0 || u_mbar_test(sm.sempty, (uint32_t)((sh + 1) & 1)))) {
+          const int ta = rk + kFGS * (ua / kFChunks), c = ua % kFChunks;
+          const int sh = ua >> 2;           // drains so far = halves started
+          const int tdone = min(hb >> 1, *reinterpret_cast<volatile int*>(sm.zdone));
+          if (ta - tdone < a.window && u_mbar_test(&sm.afull[ua % nsa], (uint32_t)((ua / nsa) & 1)) &&
+              ((c & 3) || sh == 0 || u_mbar_test(sm.sempty, (uint32_t)((sh + 1) & 1)))) {
             u_fence_after();
             if (c == 0) f_trace(a, ta, 1);
-            const uint32_t base = u_smem(sm.stages + (size_t)(ua % kFSA) * kFStageBytes);
+            if (c == 4) f_trace(a, ta, 7);
+            if (c == 7) f_trace(a, ta, 12);
+            const uint32_t base = u_smem(sm.stages + (size_t)(ua % nsa) * kFStageA);
             const uint32_t acc = tmem + kFColS;
 #pragma unroll
-            for (int kk = 0; kk < kFDS / 16; ++kk) {
+            for (int kk = 0; kk < kFChunkD / 16; ++kk) {
               if ((a.dbg & 1) && kk > 0) break;
-              const uint32_t off = (uint32_t)(kk >> 2) * 8192 + (uint32_t)(kk & 3) * 32;
-              const uint64_t bh = u_desc(base + off, 16, 1024);
-              const uint64_t bl = u_desc(base + 16384 + off, 16, 1024);
-              const uint32_t xa = tmem + kFColX + (uint32_t)(c * 8 + kk) * 8;
-              u_mma_ts(acc, xa, bh, idA, ((c & 1) || kk > 0) ? 1u : 0u);
+              const uint64_t bh = u_desc(base + kk * 32, 16, 1024);
+              const uint64_t bl = u_desc(base + 16384 + kk * 32, 16, 1024);
+              const uint32_t xa = tmem + kFColX + (uint32_t)(c * 4 + kk) * 8;
+              u_mma_ts(acc, xa, bh, idA, ((c & 3) || kk > 0) ? 1u : 0u);
               u_mma_ts(acc, xa, bl, idA, 1u);
             }
-            if (c & 1) u_commit(sm.sfull);
-            u_commit(&sm.aempty[ua % kFSA]);
+            if ((c & 3) == 3) u_commit(sm.sfull);
+            u_commit(&sm.aempty[ua % nsa]);
             ++ua;
             did = true;
           }
         }
         if (did) idle = 0;
-        else {
-          if (a.mma_sleep) __nanosleep(a.mma_sleep);
-          if (++idle > kFSpinLimit) f_timeout(a, 0x210, (uint32_t)ua, (uint32_t)tb);
-        }
+        else if (++idle > kFSpinLimit) f_timeout(a, 0x210, (uint32_t)ua, (uint32_t)hb);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ============================================================ query prologue, then phase-A drain
+  } else if (warp == 2) {
+    // ============================================================ phase-B producer: weights + second read of the tile
+    // The phase-B stages double as the staging area of the query prologue: no TMA into them before it is done.
+    if (lane == 0) f_wait(a, sm.xfull, 0, 0x122, 0);
+    __syncwarp();
+    int hb = 0;
+    uint32_t spin = 0;
+    while (hb < nhb) {
+      // lanes 0..7 look at the counters of the next tiles: one round trip tells how far the weights are published
+      const int t0 = hb >> 1;
+      int ok = 0;
+      if (lane < 8 && t0 + lane < ntiles) {
+        const uint32_t seq = epoch0 + (uint32_t)(t0 + lane);
+        const uint32_t c = u_ld_acquire(a.ar.counter + (seq % kFRingP));
+        ok = (int32_t)(c - (seq / kFRingP) * (uint32_t)kFUnits) >= 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      __syncwarp();                               // lane 0 issues the loads on behalf of the lanes that acquired
+      const int nready = __ffs(~m) - 1;           // consecutive published tiles from t0 on
+      if (nready == 0) {
+        if (a.poll_sleep) __nanosleep(a.poll_sleep);
+        if (++spin > kFSpinLimit) f_timeout(a, 0x400, (uint32_t)t0, 0);
+        continue;
+      }
+      spin = 0;
+      if (lane == 0) {
+        f_st_release_cta(sm.pub_upto, t0 + nready);
+        asm volatile("fence.proxy.async;" ::: "memory");      // the weights were written by generic stores of other SMs
+        const int hb_end = min(nhb, (t0 + nready) * 2);
+        for (; hb < hb_end; ++hb) {
+          const int s = hb % nsb;
+          if (hb >= nsb) f_wait(a, &sm.bempty[s], (uint32_t)(((hb / nsb) + 1) & 1), 0x121, hb);
+          if (!(hb & 1)) f_trace(a, hb >> 1, 6);
+          uint8_t* st = bstages + (size_t)s * kFStageB;
+          const uint32_t seq = epoch0 + (uint32_t)(hb >> 1);
+          const int prow = (int)(seq % kFRingP) * kFR + (hb & 1) * kFHB;
+          const int r0 = hb * kFHB;
+          u_mbar_expect_tx(&sm.bfull[s], kFStageB);
+          u_tma_2d(st, &tm_p, 0, prow, &sm.bfull[s]);
+          u_tma_2d(st + 8192, &tm_p, 64, prow, &sm.bfull[s]);
+          f_tma_2d_hint(st + 16384, &tm_hi, d0, r0, &sm.bfull[s], pol_drop);
+          f_tma_2d_hint(st + 24576, &tm_hi, d0 + 64, r0, &sm.bfull[s], pol_drop);
+          f_tma_2d_hint(st + 32768, &tm_lo, d0, r0, &sm.bfull[s], pol_drop);
+          f_tma_2d_hint(st + 40960, &tm_lo, d0 + 64, r0, &sm.bfull[s], pol_drop);
+        }
+      }
+      hb = __shfl_sync(0xffffffffu, hb, 0);
+    }
+  } else if (warp >= 4 && warp < 12) {
     const int lq = warp & 3;
+    const int set = (warp - 4) >> 2;                    // 0: warps 4-7, 1: warps 8-11
     const int part = lane >> 4;                         // lanes 0-15 hold hi parts, 16-31 lo parts of the same q
     const int q = lq * 16 + (lane & 15);
     const uint32_t tlane = tmem + ((uint32_t)(lq * 32) << 16);
-    // ---- X[:, super-slice] -> bf16 hi / lo -> tensor memory, in four chunks of 128 d staged through shared memory
-    //      (whole 512-byte rows by bulk copies, one per lane, then thread = row: a warp-wide global load of 32
-    //      different rows costs 32 L1 wavefronts per instruction); ||x_q||^2 partial of this CTA's own slice
+    // ============================================================ query prologue (8 warps)
+    // X[:, super-slice] -> bf16 hi / lo -> tensor memory: warp set s converts the 128-wide chunks 2s and 2s + 1 of its
+    // 16 query rows, staged through shared memory (whole 512-byte rows by bulk copies, one per lane, then thread =
+    // row: a warp-wide global load of 32 different rows costs 32 L1 wavefronts per instruction); ||x_q||^2 partial of
+    // this CTA's own slice
     {
       const int row0 = lq * 16;
       const int nvalid = max(0, min(16, a.Q - row0));
       const bool valid = q < a.Q;
-      auto fetch = [&](int c) {
-        uint64_t* bar = &sm.xload[lq * 2 + (c & 1)];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = set * 2 + cc;
+        uint64_t* bar = &sm.xload[(warp - 4) * 2 + cc];
         if (lane == 0) u_mbar_expect_tx(bar, (uint32_t)nvalid * (kFDS * 4));
         __syncwarp();
         if (lane < nvalid) {
           const int r = row0 + lane;
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(u_smem(xstage + ((size_t)(c & 1) * kFQ + r) * kFPitch)),
+                       ::"r"(u_smem(xstage + ((size_t)c * kFQ + r) * kFPitch)),
                          "l"(a.xq + (int64_t)r * a.D + ds0 + c * kFDS), "r"(kFDS * 4), "r"(u_smem(bar)) : "memory");
         }
-      };
-      fetch(0);
+      }
       float ss = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < kFGS; ++c) {
-        if (c + 1 < kFGS) fetch(c + 1);                 // the other buffer: its previous chunk was consumed by this warp
-        f_wait(a, &sm.xload[lq * 2 + (c & 1)], (uint32_t)((c >> 1) & 1), 0x340, c);
-        const float* xr = xstage + ((size_t)(c & 1) * kFQ + q) * kFPitch;
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = set * 2 + cc;
+        if (nvalid > 0) f_wait(a, &sm.xload[(warp - 4) * 2 + cc], 0, 0x340, c);
+        const float* xr = xstage + ((size_t)c * kFQ + q) * kFPitch;
 #pragma unroll 1
         for (int c4 = 0; c4 < kFDS / 32; ++c4) {           // 32 d = 16 columns per step
           float f[32];
@@ -382,206 +445,152 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
           if (c == rk) ss += s2;
           u_tmem_st16(tlane + kFColX + c * 64 + c4 * 16, sel);
         }
-        __syncwarp();                                   // every lane has read buffer c & 1 before it is refilled
       }
       u_tmem_st_wait();
-      if (part == 0)
+      if (part == 0 && set == (rk >> 1))
         u_ll_store(a.ar.xsq_ll + ((size_t)cta * 128 + q) * 16, ss, 0.f, launch0);
       u_fence_before();
       __syncwarp();
       if (lane == 0) u_mbar_arrive(sm.xfull);
     }
-    // ---- drain: S [128 stacked rows][64 bank rows] of an own tile, twice (after chunks 1 and 3) -> registers ->
-    //      LL lines for the level-2 work units.  Layout per (ring slot, group): [job 16][q 64][2 lines of 2 rows].
+    if (set == 0) {
+      // ========================================================== phase-A drain
+      // S [128 stacked rows][128 bank rows] of an own tile, twice (after chunks 3 and 7) -> registers -> LL lines for
+      // the level-2 work units.  Layout per (ring slot, group): [job 32][q 64][2 lines of 2 rows].
 #pragma unroll 1
-    for (int i = 0; i < nown; ++i) {
-      const int t = rk + kFGS * i;
-      float acc32[32];
+      for (int i = 0; i < nown; ++i) {
+        const int t = rk + kFGS * i;
+        float acc[64];
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int sh = i * 2 + h;
-        f_wait(a, sm.sfull, (uint32_t)(sh & 1), 0x310, t);
-        u_fence_after();
-        if (warp == 4 && lane == 0 && h == 1) f_trace(a, t, 2);
-        uint32_t r0[32], r1[32];
-        u_tmem_ld32_nowait(tlane + kFColS, r0);
-        u_tmem_ld32_nowait(tlane + kFColS + 32, r1);
-        u_tmem_ld_wait();
-        u_fence_before();
-        __syncwarp();
-        if (lane == 0) u_mbar_arrive(sm.sempty);
-        // hi-part row + lo-part row of the same query; lanes l / l+16 keep bank rows [0, 32) / [32, 64) of the tile
+        for (int h = 0; h < 2; ++h) {
+          const int sh = i * 2 + h;
+          f_wait(a, sm.sfull, (uint32_t)(sh & 1), 0x310, t);
+          u_fence_after();
+          if (warp == 4 && lane == 0) f_trace(a, t, h ? 2 : 3);
+          // hi-part row + lo-part row of the same query; lanes l / l+16 keep bank rows [64 ch, +32) / [64 ch + 32, +32)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v0 = __uint_as_float(r0[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r0[j]), 16);
-          const float v1 = __uint_as_float(r1[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r1[j]), 16);
-          const float v = part ? v1 : v0;
-          acc32[j] = h ? acc32[j] + v : v;
-        }
-      }
-      const uint32_t tag = epoch0 + (uint32_t)t;            // the tile's sequence number (gap-free over launches)
-      uint8_t* dst = a.ar.part_ll + ((size_t)(tag % kFRing) * kFMaxGroups + grp) * (size_t)(kFJobs * 2048) +
-                     (size_t)(part * 8) * 2048 + (size_t)q * 32;
-#pragma unroll
-      for (int sub = 0; sub < 8; ++sub) {
-        uint8_t* o = dst + (size_t)sub * 2048;
-        u_ll_store(o, acc32[4 * sub], acc32[4 * sub + 1], tag);
-        u_ll_store(o + 16, acc32[4 * sub + 2], acc32[4 * sub + 3], tag);
-      }
-      if (warp == 4 && lane == 0) f_trace(a, t, 5);
-    }
-  } else if (warp >= 8 && warp < 12) {
-    // ============================================================ weights -> tensor memory, z, final epilogue
-    const int lq = warp & 3;
-    const int part = lane >> 4;
-    const int q = lq * 16 + (lane & 15);
-    const uint32_t tlane = tmem + ((uint32_t)(lq * 32) << 16);
-    float z = 0.f;
-    int nb = 0;                           // next tile whose second read warp 8 has to issue
-    // the phase-B stages double as the staging area of the query prologue: no TMA into them before it is done
-    if (warp == 8 && lane == 0) f_wait(a, sm.xfull, 0, 0x122, 0);
-#pragma unroll 1
-    for (int t = 0; t < ntiles; ++t) {
-      const uint32_t seq = epoch0 + (uint32_t)t;
-      const int ring = (int)(seq % kFRing);
-      const uint32_t tag4 = (seq / kFRing) & 15u;    // the slot's previous occupant carries tag4 - 1
-      // published weights: [ring][job 16][q 64][4 rows] fp32 whose low 4 mantissa bits carry the tile's round (seq / ring):
-      // every word validates itself, so the units need no fence and no flag and the consumers no acquire -- the slot's
-      // previous occupant is exactly kFRing tiles older (ring slot = seq mod kFRing, gap-free over launches).
-      const uint32_t* wq = reinterpret_cast<const uint32_t*>(a.ar.gw) + (size_t)ring * (kFJobs * 64 * 4) + ((size_t)(part * 8) * 64 + q) * 4;
-      const int b = t & 1;
-      if (warp == 8 && lane == 0) f_trace(a, t, 12);
-      // warp 8 keeps the second reads of the next tiles in flight (L2 -> phase-B stages)
-      if (warp == 8 && lane == 0) {
-        while (nb < ntiles && nb < t + kFSB &&
-               (nb < kFSB || u_mbar_test(&sm.bempty[nb % kFSB], (uint32_t)(((nb / kFSB) + 1) & 1)))) load_b(nb++);
-      }
-      // try the full-width loads first (in steady state the weights are already there: one round trip, not two);
-      // while the tile is missing, ONE lane probes one word -- every warp spinning on 4 KiB loads would flood the L2
-      uint4 wv[8];
-      {
-        uint32_t spin = 0;
-        bool ok;
-        for (;;) {
-          ok = true;
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            wv[v] = u_ll_load(wq + (size_t)v * 64 * 4);
-            ok = ok && ((wv[v].x & 15u) == tag4) && ((wv[v].y & 15u) == tag4) && ((wv[v].z & 15u) == tag4) && ((wv[v].w & 15u) == tag4);
-          }
-          ok = __all_sync(0xffffffffu, ok);
-          if (ok) break;
-          int seen = 0;
-          do {
-            if (lane == 0) {
-              uint32_t w0;
-              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w0) : "l"(wq + (size_t)7 * 64 * 4) : "memory");
-              seen = (w0 & 15u) == tag4;
+          for (int cq = 0; cq < 4; ++cq) {                 // 32 columns at a time: ch = cq >> 1, kept by part = cq & 1
+            uint32_t r[32];
+            u_tmem_ld32_nowait(tlane + kFColS + cq * 32, r);
+            u_tmem_ld_wait();
+            if (cq == 3) {
+              u_fence_before();
+              __syncwarp();
+              if (lane == 0) u_mbar_arrive(sm.sempty);
+              if (warp == 4 && lane == 0 && h == 0) f_trace(a, t, 4);
             }
-            seen = __shfl_sync(0xffffffffu, seen, 0);
-            if (++spin > kFSpinLimit) f_timeout(a, 0x400, (uint32_t)t, tag4);
-          } while (!seen);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), 16);
+              if (part == (cq & 1)) acc[(cq >> 1) * 32 + j] = h ? acc[(cq >> 1) * 32 + j] + v : v;
+            }
+          }
         }
-      }
-      if (warp == 8 && lane == 0) {     // the tile's own second read must be on its way by now
-        while (nb <= t) {
-          if (nb >= kFSB) f_wait(a, &sm.bempty[nb % kFSB], (uint32_t)(((nb / kFSB) + 1) & 1), 0x121, nb);
-          load_b(nb++);
+        const uint32_t tag = epoch0 + (uint32_t)t;            // the tile's sequence number (gap-free over launches)
+        uint8_t* dst = a.ar.part_ll + ((size_t)(tag % kFRingL) * kFMaxGroups + grp) * (size_t)(kFJobs * 2048) + (size_t)q * 32;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+          for (int sub = 0; sub < 8; ++sub) {
+            uint8_t* o = dst + (size_t)(ch * 16 + part * 8 + sub) * 2048;
+            u_ll_store(o, acc[ch * 32 + 4 * sub], acc[ch * 32 + 4 * sub + 1], tag);
+            u_ll_store(o + 16, acc[ch * 32 + 4 * sub + 2], acc[ch * 32 + 4 * sub + 3], tag);
+          }
         }
+        if (warp == 4 && lane == 0) f_trace(a, t, 5);
       }
-      if (warp == 8 && lane == 0) f_trace(a, t, 6);
-      float own[32], oth[32];
+    } else {
+      // ========================================================== z_q from the units' partials, then the final epilogue
+      const int tid = (warp - 8) * 32 + lane;             // 0..127
+      const int zq_q = tid & 63, zhalf = tid >> 6;        // thread = (query row, half of the jobs)
+      float z = 0.f;
+#pragma unroll 1
+      for (int t = 0; t < ntiles;) {
+        int upto;
+        uint32_t spin = 0;
+        while ((upto = f_ld_acquire_cta(sm.pub_upto)) <= t) {
+          __nanosleep(200);
+          if (++spin > kFSpinLimit) f_timeout(a, 0x430, (uint32_t)t, 0);
+        }
+        for (; t < upto; ++t) {
+          const uint32_t seq = epoch0 + (uint32_t)t;
+          const float* zp = a.ar.gz + ((size_t)(seq % kFRingP) * kFJobs + zhalf * (kFJobs / 2)) * 64 + zq_q;
+          float v[kFJobs / 2];
 #pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        own[v * 4 + 0] = __uint_as_float(wv[v].x & ~15u); own[v * 4 + 1] = __uint_as_float(wv[v].y & ~15u);
-        own[v * 4 + 2] = __uint_as_float(wv[v].z & ~15u); own[v * 4 + 3] = __uint_as_float(wv[v].w & ~15u);
+          for (int j = 0; j < kFJobs / 2; ++j) {
+            uint32_t w;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(zp + (size_t)j * 64) : "memory");
+            v[j] = __uint_as_float(w);
+          }
+#pragma unroll
+          for (int j = 0; j < kFJobs / 2; ++j) z += v[j];
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");      // every z thread has read the slots of the tiles < t
+        if (tid == 0) f_st_release_cta(sm.zdone, t);
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) oth[j] = __shfl_xor_sync(0xffffffffu, own[j], 16);
-      uint32_t pk[32];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {            // rows 0..31 of the tile
-        const float k0 = part ? oth[2 * j] : own[2 * j], k1 = part ? oth[2 * j + 1] : own[2 * j + 1];
-        z += k0; z += k1;
-        const float h0 = f_bf16_hi(k0), h1 = f_bf16_hi(k1);
-        pk[j] = part ? f_pack_bf16(k0 - h0, k1 - h1) : f_pack_bf16(h0, h1);
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {            // rows 32..63
-        const float k0 = part ? own[2 * j] : oth[2 * j], k1 = part ? own[2 * j + 1] : oth[2 * j + 1];
-        z += k0; z += k1;
-        const float h0 = f_bf16_hi(k0), h1 = f_bf16_hi(k1);
-        pk[16 + j] = part ? f_pack_bf16(k0 - h0, k1 - h1) : f_pack_bf16(h0, h1);
-      }
-      if (warp == 8 && lane == 0) f_trace(a, t, 13);
-      if (t >= 2) { f_wait(a, &sm.pempty[b], (uint32_t)(((t >> 1) + 1) & 1), 0x410, t); u_fence_after(); }
-      if (warp == 8 && lane == 0) f_trace(a, t, 14);
-      u_tmem_st32(tlane + kFColP + (uint32_t)b * 32, pk);
-      u_tmem_st_wait();
-      u_fence_before();
-      __syncwarp();
-      if (lane == 0) u_mbar_arrive(&sm.pfull[b]);
-      if (warp == 8 && lane == 0) f_trace(a, t, 7);
-    }
+      sm.xsq_half[tid] = z;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (tid < 64) sm.zq[tid] = sm.xsq_half[tid] + sm.xsq_half[64 + tid];
+      asm volatile("bar.sync 2, 128;" ::: "memory");
 
-    // ---- final epilogue: num[q][slice] from tensor memory -> shared memory (thread = row) -> whole 512-byte rows
-    f_wait(a, sm.accfull, 0, 0x420, ntiles);
-    u_fence_after();
-    {
-      float* er = estage + (size_t)q * kFPitch + part * 16;
+      // ---- final epilogue: TMEM lane = d within the slice, column = query row (hi-part sums | lo-part sums)
+      f_wait(a, sm.accfull, 0, 0x420, ntiles);
+      u_fence_after();
+      const int nrows = min(a.Q, kFQ);
+      const int64_t d = (int64_t)d0 + lq * 32 + lane;
+      float msum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < kFDS / 32; ++c) {
-        uint32_t r[32];
-        u_tmem_ld32_nowait(tlane + kFColAcc + c * 32, r);
-        u_tmem_ld_wait();
-        float v[16];
+      for (int c = 0; c < kFQ / 32; ++c) {
+        float va[32];
+        {
+          float vb[32];
+          u_tmem_ld32(tlane + kFColAcc + (uint32_t)(c * 32), va);            // hi*P_hi + lo*P_hi, queries [32c, 32c+32)
+          u_tmem_ld32(tlane + kFColAcc + (uint32_t)(kFQ + c * 32), vb);      // hi*P_lo
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float lo16 = __uint_as_float(r[j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), 16);
-          const float hi16 = __uint_as_float(r[16 + j]) + __shfl_xor_sync(0xffffffffu, __uint_as_float(r[16 + j]), 16);
-          v[j] = part ? hi16 : lo16;
+          for (int j = 0; j < 32; ++j) va[j] += vb[j];
         }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(er + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      }
-      if (part == 0) sm.xsq_half[q] = z;
-    }
-    u_fence_before();
-    asm volatile("bar.sync 2, 128;" ::: "memory");
-    const int nrows = min(a.Q, kFQ);
-    float msum = 0.f;
-#pragma unroll 1
-    for (int r = warp - 8; r < nrows; r += 4) {
-      const float4 n4 = *reinterpret_cast<const float4*>(estage + (size_t)r * kFPitch + lane * 4);
-      const int64_t o = (int64_t)r * a.D + d0 + lane * 4;
-      if (a.num_out) *reinterpret_cast<float4*>(a.num_out + o) = n4;
-      if (a.epi.fused) {
-        const float denom = sm.xsq_half[r] + a.epi.eps;
-        const float4 g4 = make_float4(n4.x / denom, n4.y / denom, n4.z / denom, n4.w / denom);
-        msum += fminf(fmaxf(g4.x, -1e10f), 1e10f) + fminf(fmaxf(g4.y, -1e10f), 1e10f) +
-                fminf(fmaxf(g4.z, -1e10f), 1e10f) + fminf(fmaxf(g4.w, -1e10f), 1e10f);
-        if (a.epi.neg_out) *reinterpret_cast<float4*>(a.epi.neg_out + o) = g4;
-        if (a.epi.x0) {
-          float4 x4 = __ldcg(reinterpret_cast<const float4*>(a.epi.x0 + o));
-          x4.x = fmaf(-a.epi.scale, g4.x, x4.x); x4.y = fmaf(-a.epi.scale, g4.y, x4.y);
-          x4.z = fmaf(-a.epi.scale, g4.z, x4.z); x4.w = fmaf(-a.epi.scale, g4.w, x4.w);
-          *reinterpret_cast<float4*>(a.epi.x0 + o) = x4;
-        }
-      }
-    }
-    if (cta == 0) {
-      for (int r = (warp - 8) * 32 + lane; r < nrows; r += 128) {
-        const float zr = sm.xsq_half[r], denom = zr + a.epi.eps;
-        if (a.z_out) a.z_out[r] = zr;
         if (a.epi.fused) {
-          if (a.epi.denom_out) a.epi.denom_out[r] = denom;
-          if (a.epi.gate_out) a.epi.gate_out[r] = (!(a.epi.flags & SDN_EPI_GATE) || denom > a.epi.gate_thr) ? 1 : 0;
+          // all loads of the chunk first: the stores below may alias them as far as the compiler knows
+          float xv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int qq = min(c * 32 + j, nrows - 1);
+            xv[j] = a.epi.x0 ? __ldcg(a.epi.x0 + (int64_t)qq * a.D + d) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int qq = c * 32 + j;
+            if (qq < nrows) {
+              const int64_t o = (int64_t)qq * a.D + d;
+              const float n = va[j] / (sm.zq[qq] + a.epi.eps);
+              if (a.num_out) a.num_out[o] = va[j];
+              if (a.epi.neg_out) a.epi.neg_out[o] = n;
+              if (a.epi.x0) a.epi.x0[o] = fmaf(-a.epi.scale, n, xv[j]);
+              msum += fminf(fmaxf(n, -1e10f), 1e10f);
+            }
+          }
+        } else if (a.num_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int qq = c * 32 + j;
+            if (qq < nrows) a.num_out[(int64_t)qq * a.D + d] = va[j];
+          }
         }
       }
-    }
-    if (a.epi.fused && a.epi.mean_out) {
-      msum = warp_sum(msum);
-      if (lane == 0) atomicAdd(a.epi.mean_out, msum * a.epi.inv_qd);
+      if (cta == 0) {
+        for (int r = tid; r < nrows; r += 128) {
+          const float zr = sm.zq[r], denom = zr + a.epi.eps;
+          if (a.z_out) a.z_out[r] = zr;
+          if (a.epi.fused) {
+            if (a.epi.denom_out) a.epi.denom_out[r] = denom;
+            if (a.epi.gate_out) a.epi.gate_out[r] = (!(a.epi.flags & SDN_EPI_GATE) || denom > a.epi.gate_thr) ? 1 : 0;
+          }
+        }
+      }
+      if (a.epi.fused && a.epi.mean_out) {
+        msum = warp_sum(msum);
+        if (lane == 0) atomicAdd(a.epi.mean_out, msum * a.epi.inv_qd);
+      }
     }
   } else if (warp >= 12) {
     // ============================================================ level-2 work units: ||x||^2, sum over groups, exp, publish
@@ -622,25 +631,26 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
     }
     // ---- work units (tile t, rows [4j, 4j+4), half h of the 64 query rows) dealt round-robin over all 4 x #CTAs
     //      warps of this role: every warp is an independent worker (a worker blocks on its unit until the slowest
-    //      group has delivered, so the tiles between two units of one worker bound the rate: 16 here).  Lane l reads
+    //      group has delivered, so the tiles between two units of one worker bound the rate: 8 here).  Lane l reads
     //      lines l and 32 + l of the unit's 1 KiB block of every group (512 contiguous bytes per warp instruction)
     //      = (query row, row pair) twice, and sums the groups in order.
     {
       const int lh = lane & 1;
-      const int nunits = ntiles * kFJobs * 2;
+      const int nunits = ntiles * kFUnits;
       const int nworkers = nctas * 4;
 #pragma unroll 1
       for (int U = cta * 4 + ow; U < nunits; U += nworkers) {
-        const int t = U / (kFJobs * 2), rem = U - t * (kFJobs * 2);
+        const int t = U / kFUnits, rem = U - t * kFUnits;
         const int j = rem >> 1, qh = rem & 1;
         const uint32_t tag = epoch0 + (uint32_t)t;
-        const int ring = (int)(tag % kFRing);
-        const int row = t * kFR + j * kFJobRows + lh * 2;
+        const int ringl = (int)(tag % kFRingL), ringp = (int)(tag % kFRingP);
+        const int trow = j * kFJobRows + lh * 2;          // row within the tile
+        const int row = t * kFR + trow;
         // ||n||^2 of the two rows: issued before the wait, the line is cold
         const float sq0 = row < a.N ? __ldg(a.sqnorm + row) : 0.f;
         const float sq1 = row + 1 < a.N ? __ldg(a.sqnorm + row + 1) : 0.f;
         const size_t g_stride = (size_t)kFJobs * 2048;
-        const uint8_t* src0 = a.ar.part_ll + (size_t)ring * kFMaxGroups * g_stride + (size_t)j * 2048 +
+        const uint8_t* src0 = a.ar.part_ll + (size_t)ringl * kFMaxGroups * g_stride + (size_t)j * 2048 +
                               (size_t)(qh * 64 + lane) * 16;
         // A unit usually arrives long before its tile: ONE lane probes one line, with back-off, until the tile shows up
         // (every worker spinning on full-width loads saturates the L1s and L2)
@@ -682,7 +692,7 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
             }
         }
         if (ow == 0 && lane == 0) f_trace(a, t, 10);
-        const uint32_t tagbits = (tag / kFRing) & 15u;
+        __nv_bfloat16* prow = a.ar.gp + ((size_t)ringp * kFR + trow) * 128;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int q = qh * 32 + i * 16 + (lane >> 1);
@@ -693,15 +703,26 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
             if (row < a.N) k0v = expf(-dist_from_dot(xs, sq0, d0v, a.alpha, a.power) * a.inv2s2);
             if (row + 1 < a.N) k1v = expf(-dist_from_dot(xs, sq1, d1v, a.alpha, a.power) * a.inv2s2);
           }
-          // the weights carry the tile's round (seq / ring) in their low 4 mantissa bits (2^-19 relative): no fence, no
-          // flag -- each 32-bit word is valid on its own
-          const uint32_t b0 = (__float_as_uint(k0v) & ~15u) | tagbits, b1 = (__float_as_uint(k1v) & ~15u) | tagbits;
-          asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};"
-                       ::"l"(a.ar.gw + (((size_t)ring * kFJobs + j) * 64 + q) * 4 + lh * 2), "r"(b0), "r"(b1) : "memory");
+          // bf16 hi | lo, [row][hi parts of the 64 queries | lo parts]: the B operand of phase B as TMA loads it
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(k0v), h1 = __float2bfloat16_rn(k1v);
+          prow[q] = h0;
+          prow[64 + q] = __float2bfloat16_rn(k0v - __bfloat162float(h0));
+          prow[128 + q] = h1;
+          prow[192 + q] = __float2bfloat16_rn(k1v - __bfloat162float(h1));
+          // z partial of the unit: its four rows in order (two here, two in the neighbour lane)
+          float zu = k0v + k1v;
+          const float zo = __shfl_xor_sync(0xffffffffu, zu, 1);
+          if (lh == 0) a.ar.gz[((size_t)ringp * kFJobs + j) * 64 + q] = zu + zo;      // (rows 0,1) + (rows 2,3)
           if (a.k_out && q < a.Q) {
             if (row < a.N) a.k_out[(int64_t)q * a.N + row] = k0v;
             if (row + 1 < a.N) a.k_out[(int64_t)q * a.N + row + 1] = k1v;
           }
+        }
+        // release the unit: every lane's stores happen before lane 0's gpu-scope fence, which happens before the add
+        __syncwarp();
+        if (lane == 0) {
+          u_fence_gpu();
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(a.ar.counter + ringp) : "memory");
         }
         if (ow == 0 && lane == 0) f_trace(a, t, 11);
       }
@@ -716,7 +737,7 @@ k_flash(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUten
   }
   // every CTA has read the tag bases long before any CTA can get here (each contributed to the last tile)
   if (cta == 0 && threadIdx.x == 0) {
-    *reinterpret_cast<volatile uint32_t*>(a.ar.epoch) = epoch0 + (uint32_t)ntiles;      // gap-free: ring slot = seq mod kFRing
+    *reinterpret_cast<volatile uint32_t*>(a.ar.epoch) = epoch0 + (uint32_t)ntiles;      // gap-free: ring slot = seq mod ring
     *reinterpret_cast<volatile uint32_t*>(a.ar.epoch + 1) = launch0 + 1u;
   }
 }
@@ -730,28 +751,36 @@ struct ArenaHost {
   void* dev = nullptr;
   uint32_t* diag_host = nullptr;
   FlashArena ar{};
+  CUtensorMap tm_p{};     // weight ring [kFRingP x 128 rows][128] bf16, boxes [64 rows][64]
   int max_ctas = 0;       // co-resident CTAs of k_flash on this device
   bool coop_ok = true;
 };
 ArenaHost g_arena[kMaxDevices];
 
 constexpr size_t kXsqBytes = (size_t)kFMaxCtas * 128 * 16;
-constexpr size_t kPartBytes = (size_t)kFRing * kFMaxGroups * kFJobs * 2048;
-constexpr size_t kGwBytes = (size_t)kFRing * kFJobs * 64 * 4 * 4;
+constexpr size_t kPartBytes = (size_t)kFRingL * kFMaxGroups * kFJobs * 2048;
+constexpr size_t kGpBytes = (size_t)kFRingP * kFR * 128 * 2;
+constexpr size_t kGzBytes = (size_t)kFRingP * kFJobs * 64 * 4;
 
 int arena_get(int dev, ArenaHost** out) {
   ArenaHost& h = g_arena[dev];
   std::lock_guard<std::mutex> lk(h.mu);
   if (!h.ready) {
-    const size_t total = 256 + kXsqBytes + kPartBytes + kGwBytes;
+    const size_t total = 256 + 256 + kXsqBytes + kPartBytes + kGpBytes + kGzBytes;
     SDN_CUDA_OK(cudaMalloc(&h.dev, total));
     SDN_CUDA_OK(cudaMemset(h.dev, 0, total));
     uint8_t* p = static_cast<uint8_t*>(h.dev);
     h.ar.epoch = reinterpret_cast<uint32_t*>(p); p += 256;
+    h.ar.counter = reinterpret_cast<uint32_t*>(p); p += 256;
     h.ar.xsq_ll = p; p += kXsqBytes;
     h.ar.part_ll = p; p += kPartBytes;
-    h.ar.gw = reinterpret_cast<float*>(p); p += kGwBytes;
-    const uint32_t one[2] = {kFRing, 1};     // sequence numbers start in round 1: the zeroed rings (round-tag 0, LL tag 0) never match
+    h.ar.gp = reinterpret_cast<__nv_bfloat16*>(p); p += kGpBytes;
+    h.ar.gz = reinterpret_cast<float*>(p); p += kGzBytes;
+    {
+      const int rc = tmap_bf16_2d(&h.tm_p, h.ar.gp, (uint64_t)kFRingP * kFR, 128, kFHB, 64);
+      if (rc) return rc;
+    }
+    const uint32_t one[2] = {kFRingP, 1};    // sequence numbers start in round 1: zeroed LL tags never match, counters reach 64 x round
     SDN_CUDA_OK(cudaMemcpy(h.ar.epoch, one, sizeof(one), cudaMemcpyHostToDevice));
     void* dh = nullptr;
     if (cudaHostAlloc(&dh, 64, cudaHostAllocMapped) == cudaSuccess) {
@@ -805,8 +834,8 @@ int maps_get(int dev, const void* planes, int64_t N, int64_t D, CUtensorMap* out
   FlashMaps m{};
   const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(planes);
   int rc;
-  if ((rc = tmap_bf16_2d(&m.m[0], h, (uint64_t)N, (uint64_t)D, kFR, 64))) return rc;
-  if ((rc = tmap_bf16_2d(&m.m[1], h + N * D, (uint64_t)N, (uint64_t)D, kFR, 64))) return rc;
+  if ((rc = tmap_bf16_2d(&m.m[0], h, (uint64_t)N, (uint64_t)D, kFHB, 64))) return rc;
+  if ((rc = tmap_bf16_2d(&m.m[1], h + N * D, (uint64_t)N, (uint64_t)D, kFHB, 64))) return rc;
   m.dev = dev; m.planes = planes; m.N = N; m.D = D; m.stamp = ++g_maps_clock;
   g_maps[slot] = m;
   if (slot == g_maps_n) ++g_maps_n;
@@ -814,7 +843,7 @@ int maps_get(int dev, const void* planes, int64_t N, int64_t D, CUtensorMap* out
   return SDN_OK;
 }
 
-int launch_flash(const CUtensorMap* m, const FlashArgs& a, int nctas, bool coop, cudaStream_t st) {
+int launch_flash(const CUtensorMap* m, const CUtensorMap& mp, const FlashArgs& a, int nctas, bool coop, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nctas);
   cfg.blockDim = dim3(kFThreads);
@@ -824,7 +853,7 @@ int launch_flash(const CUtensorMap* m, const FlashArgs& a, int nctas, bool coop,
   at[0].id = cudaLaunchAttributeCooperative;     // every CTA must be resident: they wait on one another
   at[0].val.cooperative = 1;
   cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
-  return (int)cudaLaunchKernelEx(&cfg, k_flash, m[0], m[1], a);
+  return (int)cudaLaunchKernelEx(&cfg, k_flash, m[0], m[1], mp, a);
 }
 
 }  // namespace
@@ -869,16 +898,20 @@ int flash_run(const void* planes, const float* sqnorm, int64_t N, int64_t D, con
   if (h->max_ctas < nctas) return SDN_E_UNSUPPORTED;    // the grid must be co-resident
   CUtensorMap maps[2];
   if ((rc = maps_get(dev, planes, N, D, maps))) return rc;
-  static const int window = [] { const char* e = getenv("SDN_FLASH_WINDOW"); const int v = e ? atoi(e) : 0; return v >= 1 && v < kFRing ? v : kFWindow; }();
-  static const int mma_sleep = [] { const char* e = getenv("SDN_FLASH_MMA_SLEEP"); return e ? atoi(e) : 0; }();
+  // SDN_FLASH_WINDOW may only shrink the window: ring reuse is safe for window <= kFWindow
+  static const int window = [] { const char* e = getenv("SDN_FLASH_WINDOW"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 13 ? v : kFWindow; }();
+  // split of the 224 KiB stage region: nsa phase-A stages of 32 KiB, the rest phase-B stages of 48 KiB
+  static const int nsa = [] { const char* e = getenv("SDN_FLASH_NSA"); const int v = e ? atoi(e) : 0; return v >= 2 && v <= 4 ? v : 4; }();
   static const int poll_sleep = [] { const char* e = getenv("SDN_FLASH_POLL_SLEEP"); return e ? atoi(e) : 100; }();
   for (int64_t q0 = 0; q0 < Q; q0 += kFQ) {
     const int qn = (int)std::min<int64_t>(kFQ, Q - q0);
     FlashArgs a{};
-    a.xq = xq + q0 * D; a.sqnorm = sqnorm; a.Q = qn; a.N = (int)N; a.ntiles = (int)cdiv(N, kFR); a.ngroups = nctas / kFGS;
+    a.xq = xq + q0 * D; a.sqnorm = sqnorm; a.Q = qn; a.N = (int)N; a.ntiles = (int)cdiv(N, kFR); a.nhb = (int)cdiv(N, kFHB);
+    a.ngroups = nctas / kFGS;
+    a.nsa = nsa; a.nsb = std::min<int>(kFMaxStages, (int)((kFStageRegion - (uint32_t)nsa * kFStageA) / kFStageB));
     static const int dbg = [] { const char* e = getenv("SDN_FLASH_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = (unsigned)dbg;
-    a.window = window; a.mma_sleep = (unsigned)mma_sleep; a.poll_sleep = (unsigned)poll_sleep;
+    a.window = window; a.poll_sleep = (unsigned)poll_sleep;
     a.D = D; a.inv2s2 = inv2s2; a.alpha = alpha; a.power = power;
     a.num_out = num_out ? num_out + q0 * D : nullptr;
     a.z_out = z_out ? z_out + q0 : nullptr;
@@ -894,13 +927,13 @@ int flash_run(const void* planes, const float* sqnorm, int64_t N, int64_t D, con
     }
     a.ar = h->ar;
     const int pid = g_prof.begin("k_flash", st);
-    int e = launch_flash(maps, a, nctas, h->coop_ok, st);
+    int e = launch_flash(maps, h->tm_p, a, nctas, h->coop_ok, st);
     if (e != 0 && h->coop_ok) {
       // cooperative launch refused: co-residency still holds by the occupancy check above as long as nothing else
       // runs on the device
       cudaGetLastError();
       h->coop_ok = false;
-      e = launch_flash(maps, a, nctas, false, st);
+      e = launch_flash(maps, h->tm_p, a, nctas, false, st);
     }
     g_prof.end(pid, st);
     if (e != 0) return e;

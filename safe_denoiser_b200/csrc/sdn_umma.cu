@@ -72,12 +72,44 @@ __device__ __forceinline__ USmem u_carve(unsigned char* raw) {
   return s;
 }
 
+constexpr int kListCap = 32;     // significant rows per query the listed accumulate handles
+
+struct SigLists {
+  int* flags;        // [Npad/64]      row block holds a significant weight
+  int* count;        // [64]           significant rows per query (may exceed kListCap)
+  int ncount;        //                entries of `count` the start-of-pass clear covers (64 G)
+  int* dense;        // [1]            set by k_umma_zreduce when some query's weights are flat (z / kmax > cap):
+                     //                its list must overflow, so nobody builds lists or flags and phase B is dense
+  int* rows;         // [64][kListCap] their bank row indices (unsorted, first kListCap arrivals)
+  float* ks;         // [64][kListCap] their weights
+};
+
+// zeroes the lists (launched as part of k_umma_weights' grid: block 0 does it before anyone appends)
+__device__ __forceinline__ void siglist_clear(const SigLists& L, int nflags) {
+  for (int i = threadIdx.x; i < nflags; i += blockDim.x) L.flags[i] = 0;
+  if (threadIdx.x < L.ncount) L.count[threadIdx.x] = 0;
+  if (threadIdx.x == 0) *L.dense = 0;
+}
+
+// What the first query-prepare block of a pass resets before anything else of the pass runs: the significant-row
+// lists and the arrival counters of phase A's fused weights step.
+struct StartClear {
+  SigLists lists; int nflags;      // lists.flags == nullptr: no lists in this pass
+  int* counters; int ncounters;    // [row tiles + 1]
+};
+__device__ __forceinline__ void start_clear(const StartClear& c) {
+  if (c.lists.flags) siglist_clear(c.lists, c.nflags);
+  for (int i = threadIdx.x; i < c.ncounters; i += blockDim.x) c.counters[i] = 0;
+}
+
 // ------------------------------------------------------------------------------------------ query planes
 // bf16 hi/lo planes of 64 query rows: hi part of row q at plane row q, lo part at plane row lo_rows + q.
 //   one group per pass : [64 hi | 64 lo] rows = ONE stacked 128-row MMA operand           (lo_rows = 64)
 //   two groups per pass: [128 hi] [128 lo]   = two 128-row operands, group g at rows 64 g (lo_rows = 128)
 __global__ void __launch_bounds__(256)
-k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes, int lo_rows) {
+k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes, int lo_rows,
+             const StartClear clr) {
+  if (blockIdx.x == 0 && blockIdx.y == 0) start_clear(clr);
   const int q = blockIdx.y;   // 0..63
   const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (j >= D) return;
@@ -102,8 +134,9 @@ k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
 // conditioning call needs no separate query-prepare launch.  grid (D/1024, 64).
 __global__ void __launch_bounds__(256)
 k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes, int lo_rows,
-             float* __restrict__ xsq_part, float* __restrict__ zero_word) {
+             float* __restrict__ xsq_part, float* __restrict__ zero_word, const StartClear clr) {
   __shared__ float red[33];
+  if (blockIdx.x == 0 && blockIdx.y == 0) start_clear(clr);
   if (zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *zero_word = 0.f;
   const int q = blockIdx.y;
   const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
@@ -147,13 +180,165 @@ constexpr int kUChunk = 4;
 constexpr int kUThreadsA = 192;   // TMA warp, MMA warp, 4 epilogue warps
 constexpr uint32_t kAccColsA = 128;
 
+// Weights step fused into phase A (round 2): the CTA that delivers the LAST K-split partial of a row tile turns the
+// tile's dots into weights -- sums the K-split partials in split order, k = exp(-dist / 2 sigma^2), writes the weight
+// planes P [Npad][128] bf16 (hi parts in columns [0,64), lo parts in [64,128): phase B's MN-major B operand) and the
+// tile's z sums / maxima; the CTA that finishes the last tile sums those over the tiles in tile order (z, kmax, the
+// flat-regime mark).  Replaces the k_umma_weights + k_umma_zreduce launches (11.6 + 4 us at cfg3, 13.7 us for a
+// 375-row shard) by a ~3 us tail on 24 CTAs in parallel.  Arrival counters are zeroed by the query-prepare kernel.
+struct DotsTail {
+  int enabled;
+  int* tile_count;          // [row tiles] K splits that have delivered, then [1] tiles whose weights are done
+  const float* sqnorm; const float* xsq; const float* xsq_part; int xsq_nparts;
+  int N, Q, row_tiles;
+  float inv2s2, alpha; int power;
+  __nv_bfloat16* P; int64_t p_group_stride;      // [G][Npad][128]
+  int keep_from_row;        // bank rows >= this are loaded with L2 evict_last, the others evict_first (-1: no hints):
+                            // phase B starts with the rows phase A read last and finds them in the L2
+  float* zpart; int64_t zpart_stride;            // [G][row tiles][sums 64 | maxima 64]
+  float* z; float* kmax; int* dense_flag;        // [64 G], [64 G], [1] or null
+  float* k_out;                                  // [Q][N] or null
+};
+
+template <int G>
+__device__ __forceinline__ void dots_tail(const DotsTail& T, const float* __restrict__ S_T, int64_t split_stride, int ksplit,
+                                          int row0, float (*zs)[kUQ], float (*zm)[kUQ], int* s_flag, uint8_t* stage,
+                                          uint64_t* bar, float* sq_s) {
+  const int t = threadIdx.x, q = t & (kUQ - 1), rsub = t >> 6;       // 192 threads: 3 row subsets x 64 query rows
+  constexpr int kSub = kUThreadsA / kUQ;
+  // The K-split partials of the tile come into the (now idle) pipeline stages by bulk copies -- a round of R rows is
+  // ksplit contiguous pieces of R x 512 bytes: register loads from L2 were latency-bound (54 us for this step at cfg3).
+  const int R = min(kUBankTile, (int)(kPipeBytes / ((uint32_t)ksplit * kUStack * 4)));
+  const float* sst = reinterpret_cast<const float*>(stage);          // [ksplit][R][128]
+  float xs[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int Qg = min(kUQ, T.Q - g * kUQ);
+    xs[g] = 0.f;
+    if (q < Qg) {
+      if (T.xsq) {
+        xs[g] = T.xsq[g * kUQ + q];
+      } else {
+        // batches of independent loads: a loop of dependent L2 loads costs a round trip per iteration
+        const float* xp = T.xsq_part + (int64_t)g * T.xsq_nparts * kUQ;
+        for (int c0 = 0; c0 < T.xsq_nparts; c0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = c0 + u < T.xsq_nparts ? __ldcg(xp + (int64_t)(c0 + u) * kUQ + q) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) xs[g] += v[u];
+        }
+      }
+    }
+  }
+  // ||n||^2 of the tile's rows: one parallel load (a load per row inside the loop serialises on L2 latency)
+  if (t < kUBankTile) sq_s[t] = row0 + t < T.N ? __ldg(T.sqnorm + row0 + t) : 0.f;
+  __syncthreads();
+  float zsum[G], zmax[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) zsum[g] = zmax[g] = 0.f;
+  int round = 0;
+#pragma unroll 1
+  for (int r0 = 0; r0 < kUBankTile; r0 += R, ++round) {
+    const int nr = min(R, kUBankTile - r0);
+    if (t == 0) {
+      const uint32_t bytes = (uint32_t)nr * kUStack * 4;
+      u_mbar_expect_tx(bar, bytes * (uint32_t)ksplit);
+      for (int sp = 0; sp < ksplit; ++sp)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(u_smem(stage + (size_t)sp * R * kUStack * 4)),
+                       "l"(S_T + (int64_t)sp * split_stride + (int64_t)(row0 + r0) * kUStack), "r"(bytes), "r"(u_smem(bar))
+                     : "memory");
+    }
+    u_mbar_wait(bar, (uint32_t)(round & 1));
+#pragma unroll 1
+    for (int i = rsub; i < nr; i += kSub) {
+      const int row = row0 + r0 + i;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int Qg = min(kUQ, T.Q - g * kUQ);
+        const float* sp0 = sst + (size_t)i * kUStack + (G == 1 ? q : g * kUQ + q);
+        float dot = 0.f;
+#pragma unroll 4
+        for (int sp = 0; sp < ksplit; ++sp) {
+          const float* p = sp0 + (size_t)sp * R * kUStack;
+          dot += G == 1 ? p[0] + p[kUQ] : p[0];
+        }
+        float k = 0.f;
+        if (row < T.N && q < Qg) k = expf(-dist_from_dot(xs[g], sq_s[r0 + i], dot, T.alpha, T.power) * T.inv2s2);
+        __nv_bfloat16* Pg = T.P + (int64_t)g * T.p_group_stride;
+        const __nv_bfloat16 h = __float2bfloat16_rn(k);
+        Pg[(int64_t)row * kUStack + q] = h;
+        Pg[(int64_t)row * kUStack + kUQ + q] = __float2bfloat16_rn(k - __bfloat162float(h));
+        if (T.k_out && row < T.N && q < Qg) T.k_out[(int64_t)(g * kUQ + q) * T.N + row] = k;
+        zsum[g] += k;
+        zmax[g] = fmaxf(zmax[g], k);
+      }
+    }
+    __syncthreads();                     // the stage is read out before the next round's copies land
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    zs[rsub][q] = zsum[g]; zm[rsub][q] = zmax[g];
+    __syncthreads();
+    if (t < kUQ) {
+      float a = 0.f, m = 0.f;
+#pragma unroll
+      for (int r = 0; r < kSub; ++r) { a += zs[r][t]; m = fmaxf(m, zm[r][t]); }
+      float* zp = T.zpart + (int64_t)g * T.zpart_stride + (int64_t)blockIdx.x * kUStack;
+      zp[t] = a; zp[kUQ + t] = m;
+    }
+    __syncthreads();
+  }
+  // ---- the CTA that completes the last row tile sums the tiles' partials in tile order
+  __threadfence();
+  __syncthreads();
+  if (t == 0) *s_flag = atomicAdd(T.tile_count + T.row_tiles, 1) == T.row_tiles - 1 ? 1 : 0;
+  __syncthreads();
+  if (!*s_flag) return;
+  __threadfence();
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const float* zp = T.zpart + (int64_t)g * T.zpart_stride;
+    float a = 0.f, m = 0.f;
+    for (int b0 = rsub; b0 < T.row_tiles; b0 += 8 * kSub) {
+      float va[8], vm[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = b0 + u * kSub;
+        va[u] = b < T.row_tiles ? __ldcg(zp + (int64_t)b * kUStack + q) : 0.f;
+        vm[u] = b < T.row_tiles ? __ldcg(zp + (int64_t)b * kUStack + kUQ + q) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a += va[u]; m = fmaxf(m, vm[u]); }
+    }
+    zs[rsub][q] = a; zm[rsub][q] = m;
+    __syncthreads();
+    if (t < kUQ && t < T.Q - g * kUQ) {
+      float zz = 0.f, mm = 0.f;
+#pragma unroll
+      for (int r = 0; r < kSub; ++r) { zz += zs[r][t]; mm = fmaxf(mm, zm[r][t]); }
+      T.z[g * kUQ + t] = zz;
+      T.kmax[g * kUQ + t] = mm;
+      // sum_i k_i / kmax <= (#rows with k_i >= tau kmax) + N tau: more than kListCap "effective rows" means the
+      // query's significant-row list must overflow
+      if (T.dense_flag && zz > (float)kListCap * mm) atomicOr(T.dense_flag, 1);
+    }
+    __syncthreads();
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(kUThreadsA, 1)
 k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
             const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int64_t split_stride,
-            int kblocks_total, int ksplit, int use_lo) {
+            int kblocks_total, int ksplit, int use_lo, const DotsTail tail) {
   using C = UCfg<G>;
   extern __shared__ unsigned char smem_raw[];
+  __shared__ float zs[kUThreadsA / kUQ][kUQ], zm[kUThreadsA / kUQ][kUQ];
+  __shared__ int s_flag;
+  __shared__ uint64_t tail_bar;
+  __shared__ float sq_s[kUBankTile];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kUBankTile;
@@ -162,6 +347,11 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int nkb = kb1 - kb0;
   const int nchunks = (nkb + kUChunk - 1) / kUChunk;
 
+  uint64_t bank_policy = 0;
+  if (tail.keep_from_row >= 0) {
+    if (row0 >= tail.keep_from_row) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(bank_policy));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(bank_policy));
+  }
   auto load_stage = [&](int i) {
     const int s = i % C::kStages;
     uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
@@ -169,13 +359,19 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const int kc = (kb0 + i) * kUK;
 #pragma unroll
     for (int g = 0; g < G; ++g) u_tma_2d(st + (size_t)g * kTileBytes, &tm_x, kc, g * kUStack, &sm.full[s]);
-    u_tma_2d(st + C::kHiOff, &tm_hi, kc, row0, &sm.full[s]);
-    if (use_lo) u_tma_2d(st + C::kLoOff, &tm_lo, kc, row0, &sm.full[s]);
+    if (tail.keep_from_row >= 0) {
+      u_tma_2d_hint(st + C::kHiOff, &tm_hi, kc, row0, &sm.full[s], bank_policy);
+      if (use_lo) u_tma_2d_hint(st + C::kLoOff, &tm_lo, kc, row0, &sm.full[s], bank_policy);
+    } else {
+      u_tma_2d(st + C::kHiOff, &tm_hi, kc, row0, &sm.full[s]);
+      if (use_lo) u_tma_2d(st + C::kLoOff, &tm_lo, kc, row0, &sm.full[s]);
+    }
   };
   const int npre = min(nkb, C::kStages);
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
+    u_mbar_init(&tail_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the first stages need nothing but this thread's own barriers: their HBM latency overlaps the TMEM
     // allocation and the start-up barrier (the kernel is fill/drain bound at N ~ 3000)
@@ -262,31 +458,28 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     u_fence_after();
     u_tmem_dealloc(tmem, 2 * kAccColsA);
   }
-}
-
-constexpr int kListCap = 32;     // significant rows per query the listed accumulate handles
-
-struct SigLists {
-  int* flags;        // [Npad/64]      row block holds a significant weight
-  int* count;        // [64]           significant rows per query (may exceed kListCap)
-  int* dense;        // [1]            set by k_umma_zreduce when some query's weights are flat (z / kmax > cap):
-                     //                its list must overflow, so nobody builds lists or flags and phase B is dense
-  int* rows;         // [64][kListCap] their bank row indices (unsorted, first kListCap arrivals)
-  float* ks;         // [64][kListCap] their weights
-};
-
-// zeroes the lists (launched as part of k_umma_weights' grid: block 0 does it before anyone appends)
-__device__ __forceinline__ void siglist_clear(const SigLists& L, int nflags) {
-  for (int i = threadIdx.x; i < nflags; i += blockDim.x) L.flags[i] = 0;
-  if (threadIdx.x < kUQ) L.count[threadIdx.x] = 0;
-  if (threadIdx.x == 0) *L.dense = 0;
+  if (tail.enabled) {
+    // the partial of this K split is in global memory (epilogue stores above): is this CTA the tile's last arrival?
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_flag = atomicAdd(tail.tile_count + blockIdx.x, 1) == ksplit - 1 ? 1 : 0;
+    __syncthreads();
+    if (s_flag) {
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");    // the partials were written by generic stores of other SMs
+      dots_tail<G>(tail, S_T, split_stride, ksplit, row0, zs, zm, &s_flag, sm.tiles, &tail_bar, sq_s);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ weights
-// One thread per (bank row, query row): sum the K-split partials, k = exp(-dist / 2 sigma^2), write the weight
-// planes P [Npad][128] bf16 (stacked query index contiguous: hi parts in columns [0,64), lo parts in [64,128)),
-// which phase B reads as an MN-major B operand.  Everything is coalesced; block = 4 bank rows x 64 query rows.
-constexpr int kWRows = 4;
+// Thread = (bank row, query row): sum the K-split partials in split order, k = exp(-dist / 2 sigma^2), write the
+// weight planes P [Npad][128] bf16 (stacked query index contiguous: hi parts in columns [0,64), lo parts in [64,128)),
+// which phase B reads as an MN-major B operand.  A block of 256 threads walks `rows_per_block` bank rows four at a
+// time (<= 128 blocks: every SM ingests its share of the partials at ~45 GB/s); everything is coalesced.  The block
+// that finishes last sums the per-block z partials in block order (z, kmax, the flat-regime mark): round 1 did that in
+// a second launch (k_umma_zreduce, ~4 us), and summed ||x||^2 parts in a loop of dependent L2 loads (8 of 12.7 us).
+constexpr int kWRows = 4;          // bank rows a block handles per step (and per k_umma_siglist block)
 
 // The dot of query row q is S_T[..][col0 + q] (+ S_T[..][col0 + lo_off + q] when lo_off > 0: stacked operand).
 __global__ void __launch_bounds__(kWRows * kUQ)
@@ -294,47 +487,116 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
                const float* __restrict__ sqnorm,
                const float* __restrict__ xsq, const float* __restrict__ xsq_part, int xsq_nparts, int N, int Q,
                float inv2s2, int power, float alpha, __nv_bfloat16* __restrict__ P, float* __restrict__ zpart,
-               float* __restrict__ k_out, SigLists lists, int nflags) {
-  __shared__ float zs[kWRows][kUQ];
-  if (blockIdx.x == 0 && lists.flags) siglist_clear(lists, nflags);
+               float* __restrict__ k_out, int rows_per_block, int npad, int* __restrict__ arrivals, float* __restrict__ z,
+               float* __restrict__ kmax, int* __restrict__ dense_flag) {
+  __shared__ float zs[kWRows][kUQ], zm[kWRows][kUQ];
+  __shared__ int s_last;
   const int q = threadIdx.x & (kUQ - 1);
   const int rsub = threadIdx.x >> 6;
-  const int i = blockIdx.x * kWRows + rsub;
-  const float* s = S_T + (int64_t)i * kUStack;
-  float dot = 0.f;
-#pragma unroll 4
-  for (int sp = 0; sp < ksplit; ++sp) {
-    const float* p = s + (int64_t)sp * split_stride + col0;
-    dot += lo_off > 0 ? p[q] + p[lo_off + q] : p[q];
-  }
-  float k = 0.f;
-  if (i < N && q < Q) {
-    float xs = 0.f;
-    if (xsq) {
-      xs = xsq[q];
-    } else {
-      for (int c = 0; c < xsq_nparts; ++c) xs += xsq_part[(int64_t)c * kUQ + q];
+  float zsum = 0.f, zmax = 0.f;
+  const int i0 = blockIdx.x * rows_per_block;
+  float xs = 0.f;
+  bool have_xs = false;
+#pragma unroll 1
+  for (int r = rsub; r < rows_per_block && i0 + r < npad; r += kWRows) {
+    const int i = i0 + r;
+    // every load of the row is issued before the first use: the kernel is one L2 round trip deep, not three
+    const float* s = S_T + (int64_t)i * kUStack + col0 + q;
+    float a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float* p = s + (int64_t)min(u, ksplit - 1) * split_stride;
+      a[u] = __ldg(p);
+      b[u] = lo_off > 0 ? __ldg(p + lo_off) : 0.f;
     }
-    k = expf(-dist_from_dot(xs, sqnorm[i], dot, alpha, power) * inv2s2);
+    const float sq = i < N ? __ldg(sqnorm + i) : 0.f;
+    if (!have_xs) {
+      have_xs = true;
+      if (q < Q) {
+        if (xsq) {
+          xs = xsq[q];
+        } else {
+          // batches of independent loads: `xs += load` in a plain loop is one L2 round trip per part (8 us of this
+          // kernel at D = 16384 in round 1)
+          for (int c0 = 0; c0 < xsq_nparts; c0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = c0 + u < xsq_nparts ? __ldg(xsq_part + (int64_t)(c0 + u) * kUQ + q) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) xs += v[u];
+          }
+        }
+      }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (u < ksplit) dot += lo_off > 0 ? a[u] + b[u] : a[u];
+#pragma unroll 1
+    for (int sp0 = 8; sp0 < ksplit; sp0 += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float* p = s + (int64_t)min(sp0 + u, ksplit - 1) * split_stride;
+        a[u] = __ldg(p);
+        b[u] = lo_off > 0 ? __ldg(p + lo_off) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (sp0 + u < ksplit) dot += lo_off > 0 ? a[u] + b[u] : a[u];
+    }
+    float k = 0.f;
+    if (i < N && q < Q) k = expf(-dist_from_dot(xs, sq, dot, alpha, power) * inv2s2);
+    const __nv_bfloat16 h = __float2bfloat16_rn(k);
+    P[(int64_t)i * kUStack + q] = h;
+    P[(int64_t)i * kUStack + kUQ + q] = __float2bfloat16_rn(k - __bfloat162float(h));
+    if (k_out && i < N && q < Q) k_out[(int64_t)q * N + i] = k;
+    zsum += k;
+    zmax = fmaxf(zmax, k);
   }
-  const __nv_bfloat16 h = __float2bfloat16_rn(k);
-  const __nv_bfloat16 l = __float2bfloat16_rn(k - __bfloat162float(h));
-  P[(int64_t)i * kUStack + q] = h;
-  P[(int64_t)i * kUStack + kUQ + q] = l;
-  if (k_out && i < N && q < Q) k_out[(int64_t)q * N + i] = k;
-  // z: per-block partials; k_umma_zreduce sums them in a fixed order (deterministic, no same-address atomics,
-  // and no serial tail: a "last block reduces" variant spent 16 us in one SM)
-  zs[rsub][q] = k;
+  zs[rsub][q] = zsum; zm[rsub][q] = zmax;
   __syncthreads();
   if (threadIdx.x < kUQ) {
     float t = 0.f, m = 0.f;
 #pragma unroll
     for (int r = 0; r < kWRows; ++r) {
       t += zs[r][threadIdx.x];
-      m = fmaxf(m, zs[r][threadIdx.x]);
+      m = fmaxf(m, zm[r][threadIdx.x]);
     }
     zpart[(int64_t)blockIdx.x * kUStack + threadIdx.x] = t;          // [block][0..63]  sums
     zpart[(int64_t)blockIdx.x * kUStack + kUQ + threadIdx.x] = m;    // [block][64..127] maxima
+  }
+  if (!arrivals) return;               // k_umma_zreduce sums the partials
+  // ---- the last block sums the partials in block order (deterministic)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(arrivals, 1) == (int)gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float a = 0.f, m = 0.f;
+  for (int b0 = rsub; b0 < (int)gridDim.x; b0 += 8 * kWRows) {
+    float va[8], vm[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int b = b0 + u * kWRows;
+      va[u] = b < (int)gridDim.x ? __ldcg(zpart + (int64_t)b * kUStack + q) : 0.f;
+      vm[u] = b < (int)gridDim.x ? __ldcg(zpart + (int64_t)b * kUStack + kUQ + q) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a += va[u]; m = fmaxf(m, vm[u]); }
+  }
+  __syncthreads();
+  zs[rsub][q] = a; zm[rsub][q] = m;
+  __syncthreads();
+  if (threadIdx.x < kUQ && threadIdx.x < Q) {
+    float t = 0.f, mm = 0.f;
+#pragma unroll
+    for (int r = 0; r < kWRows; ++r) { t += zs[r][threadIdx.x]; mm = fmaxf(mm, zm[r][threadIdx.x]); }
+    z[threadIdx.x] = t;
+    kmax[threadIdx.x] = mm;
+    // sum_i k_i / kmax <= (#rows with k_i >= tau kmax) + N tau: more than kListCap "effective rows" means the
+    // query's significant-row list must overflow
+    if (dense_flag && t > (float)kListCap * mm) atomicOr(dense_flag, 1);
   }
 }
 
@@ -492,6 +754,7 @@ struct AccumEpi {
   const float* z;       // null: no fused correction
   float eps, scale, gate_thr; int flags;
   float* x0; float* neg_out; float* denom_out; int32_t* gate_out; float* mean_out; float inv_qd;
+  int reverse;          // walk the row blocks from the last to the first (the rows phase A read last are still in L2)
 };
 
 // grid (D / 128, n splits).  num[q][d] (+)= sum_i P[q][i] * (hi+lo)[i][d] over this split's bank rows, for the
@@ -550,7 +813,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4 * G); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
-    for (int it = 0; it < npre; ++it) load_stage(it, it % nrb, it / nrb);
+    for (int it = 0; it < npre; ++it) load_stage(it, epi.reverse ? nrb - 1 - it % nrb : it % nrb, it / nrb);
   }
   if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * C::kAccCols);
   if (warp == 0) {
@@ -582,7 +845,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       for (int it = npre; it < ntasks * nact; ++it) {
         const int t = it / nact, j = it - t * nact;
         if (it >= C::kStages) u_mbar_wait(&sm.empty[it % C::kStages], (uint32_t)(((it / C::kStages) + 1) & 1));
-        load_stage(it, dense ? j : (int)act[j], t);
+        const int jj = epi.reverse ? nact - 1 - j : j;
+        load_stage(it, dense ? jj : (int)act[jj], t);
       }
     }
   } else if (warp == 1) {
@@ -871,7 +1135,7 @@ struct UmmaLayout {
   int ksplit;
   int nflags;          // row blocks of 64 bank rows
   int xsq_nparts;
-  size_t off_x, off_s, off_p, off_z, off_f, off_q, off_n, total;
+  size_t off_x, off_s, off_p, off_z, off_f, off_q, off_c, off_n, total;
   int nsplit;          // bank-row splits of phase B (partials in the workspace, summed in order)
   // per-group strides (elements)
   int64_t split_stride, zpart_stride;
@@ -899,6 +1163,8 @@ UmmaLayout umma_layout(int64_t Q, int64_t N, int64_t D) {
   L.off_f = o; o += (size_t)L.nflags * 4 + G * kUQ * 4 + G * kUQ * 4 + 16 + G * kUQ * kListCap * 8 + 256;
   o = (o + 255) / 256 * 256;
   L.off_q = o; o += G * L.xsq_nparts * kUQ * 4;              // ||x||^2 partials of the fused query prepare
+  o = (o + 255) / 256 * 256;
+  L.off_c = o; o += (size_t)(L.npad / kUBankTile + 2) * 4;   // arrival counters of the weights step (fused: one per row tile + 1)
   o = (o + 255) / 256 * 256;
   {
     const int dblocks = (int)(D / kUDBlock), rblocks = (int)(L.npad / kUK);
@@ -1074,48 +1340,77 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   float* xsq_part = reinterpret_cast<float*>(w + L.off_q);
   auto group_rows = [&](int g) { return (int)std::min<int64_t>(kUQ, Q - (int64_t)g * kUQ); };
 
-  // query planes (one launch per group of 64 rows)
+  // query planes (one launch per group of 64 rows); the first block also resets the pass's lists and counters
+  const int row_tiles = (int)(L.npad / kUBankTile);
+  int* const counters = reinterpret_cast<int*>(w + L.off_c);
+  // SDN_UMMA_FUSED_WEIGHTS=1: the last K-split CTA of a row tile makes the tile's weights (dots_tail) instead of the
+  // k_umma_weights + k_umma_zreduce launches.  Measured slower (cfg3: dots 41 -> 64 us against 12.7 + 4 us saved): one
+  // SM ingests the tile's K-split partials at ~45 GB/s.  Kept for tiny shards / experiments, off by default.
+  static const bool fuse_weights = [] { const char* e = getenv("SDN_UMMA_FUSED_WEIGHTS"); return e && atoi(e) != 0; }();
   int pid = g_prof.begin(xsq ? "k_umma_xprep" : "k_umma_qprep", st);
   for (int g = 0; g < G; ++g) {
+    StartClear clr{};
+    if (g == 0) {
+      if (sparse) { clr.lists = lists; clr.lists.ncount = G * kUQ; clr.nflags = nflags; }
+      clr.counters = counters; clr.ncounters = row_tiles + 2;
+    }
     const float* xg = xq + (int64_t)g * kUQ * D;
     __nv_bfloat16* pg = xpl + (int64_t)g * kUQ * D;      // hi part of the group's row 0; lo parts G * 64 rows below
     if (xsq) {
-      k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg, G * kUQ);
+      k_umma_xprep<<<dim3((unsigned)cdiv(D, 1024), kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg, G * kUQ, clr);
     } else {
       k_umma_qprep<<<dim3((unsigned)L.xsq_nparts, kUQ), 256, 0, st>>>(xg, group_rows(g), D, pg, G * kUQ,
                                                                      xsq_part + (int64_t)g * L.xsq_nparts * kUQ,
-                                                                     g == 0 ? zero_word : nullptr);
+                                                                     g == 0 ? zero_word : nullptr, clr);
     }
     SDN_LAUNCHED();
   }
   g_prof.end(pid, st);
 
-  // phase A: split K (= D) so that roughly every SM gets one task
-  const int row_tiles = (int)(L.npad / kUBankTile);
+  // phase A: split K (= D) so that roughly every SM gets one task; the last arrival of a row tile makes its weights
   const int kblocks = (int)(D / kUK);
+  DotsTail tail{};
+  if (fuse_weights) {
+    tail.enabled = 1; tail.tile_count = counters; tail.sqnorm = sqnorm; tail.xsq = xsq; tail.xsq_part = xsq_part;
+    tail.xsq_nparts = L.xsq_nparts; tail.N = (int)N; tail.Q = (int)Q; tail.row_tiles = row_tiles;
+    tail.inv2s2 = inv2s2; tail.alpha = alpha; tail.power = power;
+    tail.P = P; tail.p_group_stride = L.npad * kUStack; tail.zpart = zpart; tail.zpart_stride = L.zpart_stride;
+    tail.z = z; tail.kmax = kmax; tail.dense_flag = sparse ? lists.dense : nullptr; tail.k_out = k_out;
+  }
+  // L2 carry-over between the phases: the last `keep` MB of the bank that phase A streams stay in the L2 (evict_last)
+  // and phase B reads them first
+  static const int keep_mb = [] { const char* e = getenv("SDN_UMMA_L2KEEP_MB"); return e ? atoi(e) : 0; }();
+  tail.keep_from_row = -1;
+  const bool l2keep = keep_mb > 0 && (num || epi) && L.nsplit == 1;
+  if (l2keep) {
+    const int64_t keep_rows = std::min<int64_t>(L.npad, (int64_t)keep_mb * 1000000 / (D * 4));
+    tail.keep_from_row = (int)((L.npad - keep_rows) / kUBankTile * kUBankTile);
+  }
   pid = g_prof.begin("k_umma_dots", st);
   if (G == 1)
     k_umma_dots<1><<<dim3(row_tiles, L.ksplit), kUThreadsA, kUSmemBytes, st>>>(
-        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1);
+        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
   else
     k_umma_dots<2><<<dim3(row_tiles, L.ksplit), kUThreadsA, kUSmemBytes, st>>>(
-        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1);
+        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
 
-  // weights, z, lists: per group
-  pid = g_prof.begin("k_umma_weights", st);
-  for (int g = 0; g < G; ++g) {
-    SigLists lw{};                 // what the weights kernel clears before anyone appends
-    if (sparse) { lw.flags = lists.flags; lw.count = lists.count + g * kUQ; lw.dense = lists.dense; }
-    k_umma_weights<<<(unsigned)(L.npad / kWRows), kWRows * kUQ, 0, st>>>(
+  // weights, z, lists: per group (unless the fused step is on)
+  pid = g_prof.begin(fuse_weights ? "k_umma_siglist" : "k_umma_weights", st);
+  for (int g = 0; g < G && !fuse_weights; ++g) {
+    // one bank row per thread: few fat blocks (rows in a loop, last block sums z) measured slower -- 8 warps per SM do
+    // not hide the L2 latency of the partial loads (14.7 us at cfg3 against 5 + 4 us for this kernel + k_umma_zreduce)
+    const int rpb = kWRows;
+    k_umma_weights<<<(unsigned)cdiv(L.npad, rpb), kWRows * kUQ, 0, st>>>(
         S_T, L.split_stride, L.ksplit, g * kUQ, G == 1 ? kUQ : 0, sqnorm, xsq ? xsq + g * kUQ : nullptr,
         xsq_part + (int64_t)g * L.xsq_nparts * kUQ, L.xsq_nparts, (int)N, group_rows(g), inv2s2, power, alpha,
         P + (int64_t)g * L.npad * kUStack, zpart + (int64_t)g * L.zpart_stride,
-        k_out ? k_out + (int64_t)g * kUQ * N : nullptr, lw, nflags);
+        k_out ? k_out + (int64_t)g * kUQ * N : nullptr, rpb, (int)L.npad, nullptr, z + g * kUQ, kmax + g * kUQ,
+        sparse ? lists.dense : nullptr);
     SDN_LAUNCHED();
   }
-  for (int g = 0; g < G; ++g) {
+  for (int g = 0; g < G && !fuse_weights; ++g) {
     k_umma_zreduce<<<(unsigned)group_rows(g), 256, 0, st>>>(zpart + (int64_t)g * L.zpart_stride, (int)(L.npad / kWRows),
                                                            z + g * kUQ, kmax + g * kUQ, sparse ? lists.dense : nullptr);
     SDN_LAUNCHED();
@@ -1141,6 +1436,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     if (nsplit != 1) return SDN_E_UNSUPPORTED;
     e = *epi;
   }
+  e.reverse = l2keep ? 1 : 0;
   float* const part = reinterpret_cast<float*>(w + L.off_n);
   if (sparse) {
     pid = g_prof.begin("k_umma_listed_accum", st);
