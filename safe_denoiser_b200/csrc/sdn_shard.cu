@@ -81,6 +81,21 @@ __global__ void __launch_bounds__(256) k_shard_merge_correct(const MergeArgs a) 
   if (tid < a.world) spin_until(a.sig[a.rank] + tid, epoch, a.timeout_ns, a.counter + 1);
   __syncthreads();
 
+  // ---- my D-slice, in float4 units.  The peer loads of the first (usually only) iteration are issued BEFORE the
+  // ---- z loads and the block barrier below, so that one NVLink round trip (~2.5 us) covers both.
+  const int64_t v_all = a.D / 4;
+  const int64_t v0 = v_all * a.rank / a.world, v1 = v_all * (a.rank + 1) / a.world;
+  int64_t v = v0 + (int64_t)blockIdx.x * 256 + tid;
+  float4 t[kMaxRanks];
+  auto load_peers = [&](int64_t vv) {
+    const int64_t o = q * a.D + vv * 4;
+    // all peer loads in flight at once (an NVLink load is ~2 us; issued one after the other they dominated the
+    // kernel), summed in rank order below
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p)
+      t[p] = (p < a.world) ? __ldcv(reinterpret_cast<const float4*>(a.packed[p] + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (v < v1) load_peers(v);
   if (tid == 0) {
     float zp[kMaxRanks];
 #pragma unroll
@@ -97,18 +112,8 @@ __global__ void __launch_bounds__(256) k_shard_merge_correct(const MergeArgs a) 
   }
   __syncthreads();
   const float denom = s_denom;
-
-  // ---- my D-slice, in float4 units
-  const int64_t v_all = a.D / 4;
-  const int64_t v0 = v_all * a.rank / a.world, v1 = v_all * (a.rank + 1) / a.world;
-  for (int64_t v = v0 + (int64_t)blockIdx.x * 256 + tid; v < v1; v += (int64_t)gridDim.x * 256) {
+  while (v < v1) {
     const int64_t o = q * a.D + v * 4;
-    // all peer loads in flight at once (an NVLink load is ~2 us; issued one after the other they dominated the
-    // kernel), then summed in rank order
-    float4 t[kMaxRanks];
-#pragma unroll
-    for (int p = 0; p < kMaxRanks; ++p)
-      t[p] = (p < a.world) ? __ldcv(reinterpret_cast<const float4*>(a.packed[p] + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int p = 0; p < kMaxRanks; ++p) { s.x += t[p].x; s.y += t[p].y; s.z += t[p].z; s.w += t[p].w; }
@@ -121,6 +126,8 @@ __global__ void __launch_bounds__(256) k_shard_merge_correct(const MergeArgs a) 
 #pragma unroll
     for (int p = 0; p < kMaxRanks; ++p)
       if (p < a.world) *reinterpret_cast<float4*>(a.out[p] + o) = r;
+    v += (int64_t)gridDim.x * 256;
+    if (v < v1) load_peers(v);
   }
 
   // ---- barrier 2: my stores have landed everywhere; leave only when every peer's stores have landed here

@@ -24,7 +24,6 @@ namespace sdn {
 constexpr int kStCompute = 512;               // compute threads
 constexpr int kStCWarps = kStCompute / 32;    // 16 compute warps
 constexpr int kStThreads = kStCompute + 64;   // + TMA producer warp + weights warp
-constexpr int kStStages = 6;
 constexpr int kStMaxCluster = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,37 +120,46 @@ struct StreamArgs {
   float* zero_word;  // optional scalar cleared by CTA 0 (the logging mean of the fused epilogue), or null
 };
 
-template <int Q, int VPT, int TN>
+template <int Q, int VPT, int TN, int kStStages, int LAG>
 constexpr size_t stream_smem_bytes() {
   constexpr size_t slice = (size_t)VPT * kStCompute * 4;
   constexpr size_t V = (size_t)TN * Q;
+  constexpr size_t SL = LAG + 2;             // slots of every hand-off between phase 1 and phase 2 (>= 3)
   return kStStages * TN * slice * 4          // tile ring
-         + 2 * kStCWarps * V * 4             // per-warp partials, double buffered
-         + 3 * kStMaxCluster * V * 4         // receive slots
-         + 2 * V * 4                         // k of the tiles being accumulated, double buffered
+         + SL * kStCWarps * V * 4            // per-warp partials
+         + SL * kStMaxCluster * V * 4        // receive slots
+         + SL * V * 4                        // k of the tiles being accumulated
          + 64 * 4                            // z reduction scratch
          + kStMaxCluster * 8 * 4             // per-CTA ||x slice||^2 partials
-         + (2 * kStStages + 2 + 2 + 3) * 8 + 64;   // mbarriers + alignment slack
+         + (2 * kStStages + 3 * SL) * 8 + 64;      // mbarriers + alignment slack
 }
 
 // Warp roles: warps [0, 16) compute, warp 16 lane 0 issues the TMA bulk copies, warp 17 lanes [0, V) turn
 // partial dots into weights.  All hand-offs are mbarriers; there is no __syncthreads in the loop.
-template <int Q, int VPT, int TN>
+// kStStages x TN rows x slice = 192 KiB of tiles in every instance.  Round 2: the DSMEM exchange is one ~1.2 us round
+// trip per TILE and only one tile of phase 1 overlaps it, so tiles of one or two rows (TN = 1, 2 with six stages) made
+// the kernel latency-bound -- 0.49 of the HBM roofline at Q = 1, N = 3000 (a 32 KiB tile per CTA lasts 0.7 us at full
+// rate).  Three stages of TN = 4 rows x 16 KiB (VPT = 2, clusters of 4) carry 64 KiB per exchange instead.
+// LAG = tiles between phase 1 and phase 2 of a tile: the exchange of tile t overlaps phase 1 of the next LAG tiles (and
+// phase 2 of the previous ones); every hand-off has LAG + 2 slots (a peer or the compute warps may be that far ahead).
+template <int Q, int VPT, int TN, int kStStages, int LAG>
 __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
   constexpr int V = TN * Q;
+  constexpr int SL = LAG + 2;
+  static_assert(LAG >= 1 && LAG < kStStages, "phase 2 must free stages before the ring wraps");
   constexpr int SLICE = VPT * kStCompute * 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tiles = reinterpret_cast<float*>(smem_raw);                 // [stages][TN][SLICE]
-  float* wp = tiles + (size_t)kStStages * TN * SLICE;                 // [2][cwarps][V]
-  float* recv = wp + 2 * kStCWarps * V;                               // [3][kStMaxCluster][V]
-  float* ks = recv + 3 * kStMaxCluster * V;                           // [2][V]
-  float* zred = ks + 2 * V;                                           // [64]
+  float* wp = tiles + (size_t)kStStages * TN * SLICE;                 // [SL][cwarps][V]
+  float* recv = wp + SL * kStCWarps * V;                              // [SL][kStMaxCluster][V]
+  float* ks = recv + SL * kStMaxCluster * V;                          // [SL][V]
+  float* zred = ks + SL * V;                                          // [64]
   float* xsp = zred + 64;                                             // [kStMaxCluster][8]
   uint64_t* full = reinterpret_cast<uint64_t*>(xsp + kStMaxCluster * 8);   // [stages]  TMA landed
   uint64_t* empty = full + kStStages;                                 // [stages]  all compute warps done with the stage
-  uint64_t* pr = empty + kStStages;                                   // [2]       warp partials of a tile written
-  uint64_t* kr = pr + 2;                                              // [2]       weights of a tile written
-  uint64_t* rbar = kr + 2;                                            // [3]       peers' partials landed
+  uint64_t* pr = empty + kStStages;                                   // [SL]      warp partials of a tile written
+  uint64_t* kr = pr + SL;                                             // [SL]      weights of a tile written
+  uint64_t* rbar = kr + SL;                                           // [SL]      peers' partials landed
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t crank = cluster_rank(), csize = cluster_size();
@@ -165,8 +173,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < kStStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kStCWarps); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&pr[s], kStCWarps * V); mbar_init(&kr[s], V); }
-    for (int s = 0; s < 3; ++s) mbar_init(&rbar[s], 1);
+    for (int s = 0; s < SL; ++s) { mbar_init(&pr[s], kStCWarps * V); mbar_init(&kr[s], V); mbar_init(&rbar[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -245,27 +252,29 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
         const int64_t r0 = lo + (int64_t)t * TN;
         const int rows = (int)min((int64_t)TN, hi - r0);
         const float nsq = (r < rows) ? a.sqnorm[r0 + r] : 0.f;
-        mbar_wait(&pr[t & 1], (uint32_t)((t >> 1) & 1));
+        const int sl = t % SL;
+        const uint32_t slp = (uint32_t)((t / SL) & 1);
+        mbar_wait(&pr[sl], slp);
         float sum = 0.f;
-        const float* w0 = wp + (size_t)(t & 1) * kStCWarps * V + lane;
+        const float* w0 = wp + (size_t)sl * kStCWarps * V + lane;
 #pragma unroll
         for (int w = 0; w < kStCWarps; ++w) sum += w0[w * V];
-        if (lane == 0) mbar_expect_tx(&rbar[t % 3], csize * V * 4);
-        float* slot = recv + ((size_t)(t % 3) * kStMaxCluster + crank) * V + lane;
-        for (uint32_t peer = 0; peer < csize; ++peer) st_async_remote(slot, &rbar[t % 3], peer, sum);
-        mbar_wait(&rbar[t % 3], (uint32_t)((t / 3) & 1));     // every peer's partial of tile t has landed
+        if (lane == 0) mbar_expect_tx(&rbar[sl], csize * V * 4);
+        float* slot = recv + ((size_t)sl * kStMaxCluster + crank) * V + lane;
+        for (uint32_t peer = 0; peer < csize; ++peer) st_async_remote(slot, &rbar[sl], peer, sum);
+        mbar_wait(&rbar[sl], slp);     // every peer's partial of tile t has landed
         float k = 0.f;
         if (r < rows) {
           float dot = 0.f;
-          const float* rs = recv + (size_t)(t % 3) * kStMaxCluster * V + lane;
+          const float* rs = recv + (size_t)sl * kStMaxCluster * V + lane;
           for (uint32_t src = 0; src < csize; ++src) dot += rs[src * V];
           const float d = dist_from_dot(xs_q, nsq, dot, a.alpha, a.power);
           k = expf(-d * a.inv2s2);
           if (crank == 0 && a.k_out && q < a.q_real) a.k_out[(int64_t)q * a.N + r0 + r] = k;
         }
-        ks[(t & 1) * V + lane] = k;
+        ks[sl * V + lane] = k;
         zacc += k;
-        mbar_arrive(&kr[t & 1]);
+        mbar_arrive(&kr[sl]);
       }
       if (crank == 0) zred[lane] = zacc;
     }
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
         acc[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    for (int t = 0; t <= ntiles; ++t) {
+    for (int t = 0; t < ntiles + LAG; ++t) {
       if (t < ntiles) {
         // ---------------- phase 1: partial dots of tile t ----------------
         const int s = t % kStStages;
@@ -319,18 +328,18 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
         }
         warp_reduce_scatter<V>(part, lane);
         if (warp_value_owner<V>(lane)) {
-          wp[((size_t)(t & 1) * kStCWarps + warp) * V + warp_value_index<V>(lane)] = part[0];
-          mbar_arrive(&pr[t & 1]);
+          wp[((size_t)(t % SL) * kStCWarps + warp) * V + warp_value_index<V>(lane)] = part[0];
+          mbar_arrive(&pr[t % SL]);
         }
       }
-      if (t > 0) {
-        // ---------------- phase 2: accumulate tile t-1 with its weights ----------------
-        const int tp = t - 1;
+      if (t >= LAG) {
+        // ---------------- phase 2: accumulate tile t-LAG with its weights ----------------
+        const int tp = t - LAG;
         const int s = tp % kStStages;
         const int rows = (int)min((int64_t)TN, hi - (lo + (int64_t)tp * TN));
-        mbar_wait(&kr[tp & 1], (uint32_t)((tp >> 1) & 1));
+        mbar_wait(&kr[tp % SL], (uint32_t)((tp / SL) & 1));
         const float* tile = tiles + (size_t)s * TN * SLICE;
-        const float* kt = ks + (tp & 1) * V;
+        const float* kt = ks + (tp % SL) * V;
 #pragma unroll
         for (int r = 0; r < TN; ++r) {
           if (r < rows) {
@@ -398,7 +407,13 @@ k_stream_reduce(const float* __restrict__ part_num, const float* __restrict__ pa
   }
   if (blockIdx.x == 0 && threadIdx.x < Q) {
     float t = 0.f;
-    for (int c = 0; c < ncl; ++c) t += part_z[(int64_t)c * Q + threadIdx.x];
+    for (int c0 = 0; c0 < ncl; c0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = c0 + u < ncl ? __ldg(part_z + (int64_t)(c0 + u) * Q + threadIdx.x) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t += v[u];
+    }
     z[threadIdx.x] = t;
   }
 }
@@ -418,8 +433,15 @@ __global__ void __launch_bounds__(256) k_stream_reduce_correct(const ReduceCorre
   const int64_t q = blockIdx.y;
   const int64_t QD = (int64_t)a.Q * a.D;
   const int64_t j = ((int64_t)blockIdx.x * 32 + col) * 4;
+  // batches of independent loads, summed in cluster order: `z += load` in a plain loop is an L2 round trip per cluster
   float z = 0.f;
-  for (int c = 0; c < a.ncl; ++c) z += a.part_z[(int64_t)c * a.Q + q];
+  for (int c0 = 0; c0 < a.ncl; c0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = c0 + u < a.ncl ? __ldg(a.part_z + (int64_t)(c0 + u) * a.Q + q) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) z += v[u];
+  }
   const float denom = z + a.eps;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (a.z_out) a.z_out[q] = z;
@@ -428,10 +450,13 @@ __global__ void __launch_bounds__(256) k_stream_reduce_correct(const ReduceCorre
   }
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (j < a.D) {
-#pragma unroll 4
-    for (int c = grp; c < a.ncl; c += 8) {
-      const float4 p = ld_stream4(a.part_num + (int64_t)c * QD + q * a.D + j);
-      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    for (int c0 = grp; c0 < a.ncl; c0 += 64) {
+      float4 p[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        p[u] = c0 + 8 * u < a.ncl ? ld_stream4(a.part_num + (int64_t)(c0 + 8 * u) * QD + q * a.D + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += p[u].x; s.y += p[u].y; s.z += p[u].z; s.w += p[u].w; }
     }
   }
   sh[grp][col] = s;
@@ -466,7 +491,7 @@ __global__ void __launch_bounds__(256) k_stream_reduce_correct(const ReduceCorre
 
 // ------------------------------------------------------------------------------------------ host side
 struct StreamPlan {
-  int qt = 0, vpt = 0, tn = 0, cs = 0;   // template instance and cluster size
+  int qt = 0, vpt = 0, tn = 0, ns = 0, lag = 1, cs = 0;   // template instance and cluster size
   bool ok = false;
 };
 
@@ -476,7 +501,8 @@ static StreamPlan plan_stream(int64_t Q, int64_t N, int64_t D) {
   p.qt = Q <= 1 ? 1 : (Q <= 2 ? 2 : (Q <= 4 ? 4 : 8));
   // slice = vpt * 2048 floats, cluster size = D / slice must be a power of two in [1, 8]
   static const int forced_vpt = [] { const char* e = getenv("SDN_STREAM_VPT"); return e ? atoi(e) : 0; }();
-  for (int vpt : {4, 2, 1}) {
+  static const int legacy = [] { const char* e = getenv("SDN_STREAM_LEGACY_TILES"); return e ? atoi(e) : 0; }();
+  for (int vpt : {2, 4, 1}) {
     if (forced_vpt && vpt != forced_vpt) continue;
     if (vpt > 1 && p.qt * vpt > 8) continue;
     const int64_t slice = (int64_t)vpt * kStCompute * 4;
@@ -486,16 +512,28 @@ static StreamPlan plan_stream(int64_t Q, int64_t N, int64_t D) {
     p.vpt = vpt;
     p.cs = (int)cs;
     p.tn = vpt == 1 ? (p.qt == 8 ? 2 : 4) : (vpt == 2 ? 2 : 1);
+    p.ns = 6;
+    if (!legacy) {
+      if (vpt == 2) { p.tn = 4; p.ns = 3; }                  // 3 stages x 4 rows x 16 KiB
+      if (vpt == 1 && p.qt < 8) { p.tn = 8; p.ns = 3; }      // 3 x 8 x 8 KiB (Q = 8 keeps 6 x 2 x 8 KiB: 32 values per
+                                                             // exchange measured slower, 151 against 119 us at N = 3000)
+    }
+    static const int lag = [] { const char* e = getenv("SDN_STREAM_LAG"); return e ? atoi(e) : 0; }();
+    if (!legacy && lag >= 2 && lag <= 3) {
+      // deeper hand-off instead of fatter tiles: six stages of 32 KiB (Q = 8: 16 or 32 KiB), phase 2 trails by `lag` tiles
+      if (vpt == 2) { p.tn = 2; p.ns = 6; p.lag = lag; }
+      if (vpt == 1 && p.qt == 8) { p.tn = getenv("SDN_STREAM_Q8_TN4") ? 4 : 2; p.ns = 6; p.lag = p.tn == 4 ? 2 : lag; }
+    }
     p.ok = true;
     return p;
   }
   return p;
 }
 
-template <int Q, int VPT, int TN>
+template <int Q, int VPT, int TN, int NS, int LAG>
 static int launch_stream_t(const StreamArgs& a, int cs, int max_clusters_hint, int* ncl_out, cudaStream_t st) {
-  auto kern = k_stream<Q, VPT, TN>;
-  constexpr size_t smem = stream_smem_bytes<Q, VPT, TN>();
+  auto kern = k_stream<Q, VPT, TN, NS, LAG>;
+  constexpr size_t smem = stream_smem_bytes<Q, VPT, TN, NS, LAG>();
   static std::atomic<bool> configured[kMaxDevices];
   static std::atomic<int> max_clusters_of[kMaxDevices][kStMaxCluster + 1];
   const int dev = device_slot();
@@ -560,11 +598,16 @@ static int stream_launch(const float* bank, const float* sqnorm, int64_t N, int6
   a.part_z = a.part_num + (size_t)hint * Q * D;
   int ncl = 0, rc = SDN_E_UNSUPPORTED;
   int pid = g_prof.begin("k_stream", st);
-#define SDN_ST_CASE(QQ, VV, TT) \
-  if (p.qt == QQ && p.vpt == VV && p.tn == TT) rc = launch_stream_t<QQ, VV, TT>(a, p.cs, hint, &ncl, st);
-  SDN_ST_CASE(1, 1, 4) SDN_ST_CASE(2, 1, 4) SDN_ST_CASE(4, 1, 4) SDN_ST_CASE(8, 1, 2)
-  SDN_ST_CASE(1, 2, 2) SDN_ST_CASE(2, 2, 2) SDN_ST_CASE(4, 2, 2)
-  SDN_ST_CASE(1, 4, 1) SDN_ST_CASE(2, 4, 1)
+#define SDN_ST_CASE(QQ, VV, TT, SS, LL) \
+  if (p.qt == QQ && p.vpt == VV && p.tn == TT && p.ns == SS && p.lag == LL) rc = launch_stream_t<QQ, VV, TT, SS, LL>(a, p.cs, hint, &ncl, st);
+  SDN_ST_CASE(1, 1, 4, 6, 1) SDN_ST_CASE(2, 1, 4, 6, 1) SDN_ST_CASE(4, 1, 4, 6, 1) SDN_ST_CASE(8, 1, 2, 6, 1)
+  SDN_ST_CASE(1, 2, 2, 6, 1) SDN_ST_CASE(2, 2, 2, 6, 1) SDN_ST_CASE(4, 2, 2, 6, 1)
+  SDN_ST_CASE(1, 4, 1, 6, 1) SDN_ST_CASE(2, 4, 1, 6, 1)
+  SDN_ST_CASE(1, 2, 4, 3, 1) SDN_ST_CASE(2, 2, 4, 3, 1) SDN_ST_CASE(4, 2, 4, 3, 1)
+  SDN_ST_CASE(1, 1, 8, 3, 1) SDN_ST_CASE(2, 1, 8, 3, 1) SDN_ST_CASE(4, 1, 8, 3, 1)
+  SDN_ST_CASE(1, 2, 2, 6, 2) SDN_ST_CASE(2, 2, 2, 6, 2) SDN_ST_CASE(4, 2, 2, 6, 2)
+  SDN_ST_CASE(1, 2, 2, 6, 3) SDN_ST_CASE(2, 2, 2, 6, 3) SDN_ST_CASE(4, 2, 2, 6, 3)
+  SDN_ST_CASE(8, 1, 2, 6, 2) SDN_ST_CASE(8, 1, 2, 6, 3) SDN_ST_CASE(8, 1, 4, 6, 2)
 #undef SDN_ST_CASE
   g_prof.end(pid, st);
   *a_out = a;
