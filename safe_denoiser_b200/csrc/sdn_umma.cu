@@ -52,6 +52,14 @@ struct UCfg {
   static_assert(kStages * kStageBytes == kPipeBytes, "stages must fill the pipeline area");
 };
 
+// Programmatic dependent launch (round 2): the kernels of a pass are launched with the stream-serialisation attribute,
+// every one lets its successor start at once (`launch_dependents` on entry) and waits for its predecessor's memory
+// (`wait`) only where it first needs it -- so the successor's block scheduling, barrier/TMEM set-up and the first
+// TMA loads of BANK tiles (which no kernel of the pass writes) overlap the predecessor's tail.  Both instructions are
+// no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct USmem {
   uint8_t* tiles;       // [stages][G + 2][16 KiB], 1024-byte aligned
   uint64_t* full;       // [stages]
@@ -109,6 +117,7 @@ __device__ __forceinline__ void start_clear(const StartClear& c) {
 __global__ void __launch_bounds__(256)
 k_umma_xprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes, int lo_rows,
              const StartClear clr) {
+  pdl_launch_dependents();
   if (blockIdx.x == 0 && blockIdx.y == 0) start_clear(clr);
   const int q = blockIdx.y;   // 0..63
   const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
@@ -136,6 +145,7 @@ __global__ void __launch_bounds__(256)
 k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __restrict__ planes, int lo_rows,
              float* __restrict__ xsq_part, float* __restrict__ zero_word, const StartClear clr) {
   __shared__ float red[33];
+  pdl_launch_dependents();
   if (blockIdx.x == 0 && blockIdx.y == 0) start_clear(clr);
   if (zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *zero_word = 0.f;
   const int q = blockIdx.y;
@@ -352,13 +362,17 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     if (row0 >= tail.keep_from_row) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(bank_policy));
     else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(bank_policy));
   }
-  auto load_stage = [&](int i) {
+  // what: 1 = arm the barrier + the bank tiles, 2 = the X tiles, 3 = both
+  auto load_stage = [&](int i, int what = 3) {
     const int s = i % C::kStages;
     uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
-    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     const int kc = (kb0 + i) * kUK;
+    if (what & 2) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) u_tma_2d(st + (size_t)g * kTileBytes, &tm_x, kc, g * kUStack, &sm.full[s]);
+      for (int g = 0; g < G; ++g) u_tma_2d(st + (size_t)g * kTileBytes, &tm_x, kc, g * kUStack, &sm.full[s]);
+    }
+    if (!(what & 1)) return;
+    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     if (tail.keep_from_row >= 0) {
       u_tma_2d_hint(st + C::kHiOff, &tm_hi, kc, row0, &sm.full[s], bank_policy);
       if (use_lo) u_tma_2d_hint(st + C::kLoOff, &tm_lo, kc, row0, &sm.full[s], bank_policy);
@@ -368,16 +382,21 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
   };
   const int npre = min(nkb, C::kStages);
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
     u_mbar_init(&tail_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the first stages need nothing but this thread's own barriers: their HBM latency overlaps the TMEM
-    // allocation and the start-up barrier (the kernel is fill/drain bound at N ~ 3000)
+    // allocation and the start-up barrier (the kernel is fill/drain bound at N ~ 3000); the bank tiles do not even
+    // need the query-prepare kernel to have finished, only the X tiles do
     u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
-    for (int i = 0; i < npre; ++i) load_stage(i);
+    for (int i = 0; i < npre; ++i) load_stage(i, 1);
+    pdl_wait();
+    for (int i = 0; i < npre; ++i) load_stage(i, 2);
   }
+  pdl_wait();
   if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kAccColsA);
   u_fence_before();
   __syncthreads();
@@ -491,6 +510,8 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
                float* __restrict__ kmax, int* __restrict__ dense_flag) {
   __shared__ float zs[kWRows][kUQ], zm[kWRows][kUQ];
   __shared__ int s_last;
+  pdl_launch_dependents();
+  pdl_wait();
   const int q = threadIdx.x & (kUQ - 1);
   const int rsub = threadIdx.x >> 6;
   float zsum = 0.f, zmax = 0.f;
@@ -505,9 +526,9 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
     float a[8], b[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float* p = s + (int64_t)min(u, ksplit - 1) * split_stride;
-      a[u] = __ldg(p);
-      b[u] = lo_off > 0 ? __ldg(p + lo_off) : 0.f;
+      const float* p = s + (int64_t)u * split_stride;
+      a[u] = u < ksplit ? __ldg(p) : 0.f;
+      b[u] = (u < ksplit && lo_off > 0) ? __ldg(p + lo_off) : 0.f;
     }
     const float sq = i < N ? __ldg(sqnorm + i) : 0.f;
     if (!have_xs) {
@@ -536,9 +557,9 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
     for (int sp0 = 8; sp0 < ksplit; sp0 += 8) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float* p = s + (int64_t)min(sp0 + u, ksplit - 1) * split_stride;
-        a[u] = __ldg(p);
-        b[u] = lo_off > 0 ? __ldg(p + lo_off) : 0.f;
+        const float* p = s + (int64_t)(sp0 + u) * split_stride;
+        a[u] = sp0 + u < ksplit ? __ldg(p) : 0.f;
+        b[u] = (sp0 + u < ksplit && lo_off > 0) ? __ldg(p + lo_off) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
@@ -606,6 +627,8 @@ k_umma_zreduce(const float* __restrict__ zpart, int nblocks, float* __restrict__
                int* __restrict__ dense_flag) {
   __shared__ float red[33];
   __shared__ float mx[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int q = blockIdx.x;
   float t = 0.f, m = 0.f;
   for (int b = threadIdx.x; b < nblocks; b += 256) {
@@ -766,6 +789,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
              int rblocks_total, int nsplit, int64_t split_stride, int use_lo, int p_group_rows, const int* rowflags,
              const int* __restrict__ list_count, const int* __restrict__ dense_flag, const AccumEpi epi) {
   using C = UCfg<G>;
+  pdl_launch_dependents();
+  if (dense_flag || list_count || rowflags) pdl_wait();          // the lists come from the kernels before this one
   if (dense_flag && __ldg(dense_flag)) {
     rowflags = nullptr;                                          // flat regime: no flags were built
   } else if (list_count && siglist_all_short(list_count, Q)) {
@@ -785,18 +810,22 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   const int ntasks = (dblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   // stage `it` <- row block i of this split, d-block task t
-  auto load_stage = [&](int it, int i, int t) {
+  // what: 1 = arm the barrier + the bank tiles, 2 = the weight tiles (made by the kernels before this one), 3 = both
+  auto load_stage = [&](int it, int i, int t, int what = 3) {
     const int d0 = ((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock;
     const int s = it % C::kStages;
     uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
-    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     const int rc = (rb0 + i) * kUK;                   // first bank row of this block
     // P tiles: per group two boxes of [64 rows][64 stacked q] (hi parts, lo parts), 8 KiB apart
+    if (what & 2) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      u_tma_2d(st + (size_t)g * kTileBytes, &tm_p, 0, g * p_group_rows + rc, &sm.full[s]);
-      u_tma_2d(st + (size_t)g * kTileBytes + 8192, &tm_p, 64, g * p_group_rows + rc, &sm.full[s]);
+      for (int g = 0; g < G; ++g) {
+        u_tma_2d(st + (size_t)g * kTileBytes, &tm_p, 0, g * p_group_rows + rc, &sm.full[s]);
+        u_tma_2d(st + (size_t)g * kTileBytes + 8192, &tm_p, 64, g * p_group_rows + rc, &sm.full[s]);
+      }
     }
+    if (!(what & 1)) return;
+    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart
     u_tma_2d(st + C::kHiOff, &tm_hi, d0, rc, &sm.full[s]);
     u_tma_2d(st + C::kHiOff + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
@@ -813,8 +842,12 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4 * G); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
-    for (int it = 0; it < npre; ++it) load_stage(it, epi.reverse ? nrb - 1 - it % nrb : it % nrb, it / nrb);
+    // the bank tiles of the first stages do not depend on the weights: they stream while the weights kernels finish
+    for (int it = 0; it < npre; ++it) load_stage(it, epi.reverse ? nrb - 1 - it % nrb : it % nrb, it / nrb, 1);
+    pdl_wait();
+    for (int it = 0; it < npre; ++it) load_stage(it, epi.reverse ? nrb - 1 - it % nrb : it % nrb, it / nrb, 2);
   }
+  pdl_wait();
   if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * C::kAccCols);
   if (warp == 0) {
     // compact the list of row blocks that hold a non-negligible weight (dense when no flags are given)
@@ -1235,6 +1268,23 @@ int umma_conditioning(const void* planes, const float* sqnorm, int64_t N, int64_
 }
 
 namespace {
+// Launch with (or without) the programmatic-stream-serialisation attribute: the kernel may start before the previous
+// kernel of the stream has finished and orders itself with griddepcontrol.wait (pdl_wait above).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SDN_PDL"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+
 template <int G>
 int configure_kernels() {
   SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_dots<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
@@ -1248,19 +1298,17 @@ struct AccumLaunch {
   float* num; int64_t D; int64_t split_stride; int Q, rblocks, nsplit, use_lo, p_group_rows;
   const int* flags; const int* count; const int* dense;
   AccumEpi e;
-  int gridx; bool chunked;
+  int gridx; bool chunked; bool pdl;
 };
 template <int G>
 void launch_accum(const AccumLaunch& a, cudaStream_t st) {
   const dim3 grid(a.gridx, a.nsplit);
   if (a.chunked)
-    k_umma_accum<true, G><<<grid, UCfg<G>::kThreads, kUSmemBytes, st>>>(a.tm_p, a.tm_hi, a.tm_lo, a.num, a.D, a.Q, a.rblocks,
-                                                                      a.nsplit, a.split_stride, a.use_lo, a.p_group_rows,
-                                                                      a.flags, a.count, a.dense, a.e);
+    launch_ex(k_umma_accum<true, G>, grid, dim3(UCfg<G>::kThreads), kUSmemBytes, st, a.pdl, a.tm_p, a.tm_hi, a.tm_lo, a.num,
+              a.D, a.Q, a.rblocks, a.nsplit, a.split_stride, a.use_lo, a.p_group_rows, a.flags, a.count, a.dense, a.e);
   else
-    k_umma_accum<false, G><<<grid, UCfg<G>::kThreads, kUSmemBytes, st>>>(a.tm_p, a.tm_hi, a.tm_lo, a.num, a.D, a.Q, a.rblocks,
-                                                                       a.nsplit, a.split_stride, a.use_lo, a.p_group_rows,
-                                                                       a.flags, a.count, a.dense, a.e);
+    launch_ex(k_umma_accum<false, G>, grid, dim3(UCfg<G>::kThreads), kUSmemBytes, st, a.pdl, a.tm_p, a.tm_hi, a.tm_lo, a.num,
+              a.D, a.Q, a.rblocks, a.nsplit, a.split_stride, a.use_lo, a.p_group_rows, a.flags, a.count, a.dense, a.e);
 }
 }  // namespace
 
@@ -1387,12 +1435,13 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     tail.keep_from_row = (int)((L.npad - keep_rows) / kUBankTile * kUBankTile);
   }
   pid = g_prof.begin("k_umma_dots", st);
+  const bool pdl = pdl_enabled();
   if (G == 1)
-    k_umma_dots<1><<<dim3(row_tiles, L.ksplit), kUThreadsA, kUSmemBytes, st>>>(
-        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
+    launch_ex(k_umma_dots<1>, dim3(row_tiles, L.ksplit), dim3(kUThreadsA), kUSmemBytes, st, pdl,
+              tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
   else
-    k_umma_dots<2><<<dim3(row_tiles, L.ksplit), kUThreadsA, kUSmemBytes, st>>>(
-        tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
+    launch_ex(k_umma_dots<2>, dim3(row_tiles, L.ksplit), dim3(kUThreadsA), kUSmemBytes, st, pdl,
+              tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
 
@@ -1402,17 +1451,18 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     // one bank row per thread: few fat blocks (rows in a loop, last block sums z) measured slower -- 8 warps per SM do
     // not hide the L2 latency of the partial loads (14.7 us at cfg3 against 5 + 4 us for this kernel + k_umma_zreduce)
     const int rpb = kWRows;
-    k_umma_weights<<<(unsigned)cdiv(L.npad, rpb), kWRows * kUQ, 0, st>>>(
-        S_T, L.split_stride, L.ksplit, g * kUQ, G == 1 ? kUQ : 0, sqnorm, xsq ? xsq + g * kUQ : nullptr,
-        xsq_part + (int64_t)g * L.xsq_nparts * kUQ, L.xsq_nparts, (int)N, group_rows(g), inv2s2, power, alpha,
-        P + (int64_t)g * L.npad * kUStack, zpart + (int64_t)g * L.zpart_stride,
-        k_out ? k_out + (int64_t)g * kUQ * N : nullptr, rpb, (int)L.npad, nullptr, z + g * kUQ, kmax + g * kUQ,
-        sparse ? lists.dense : nullptr);
+    launch_ex(k_umma_weights, dim3((unsigned)cdiv(L.npad, rpb)), dim3(kWRows * kUQ), 0, st, pdl,
+              (const float*)S_T, L.split_stride, L.ksplit, g * kUQ, G == 1 ? kUQ : 0, sqnorm, xsq ? xsq + g * kUQ : nullptr,
+              (const float*)(xsq_part + (int64_t)g * L.xsq_nparts * kUQ), L.xsq_nparts, (int)N, group_rows(g), inv2s2, power,
+              alpha, P + (int64_t)g * L.npad * kUStack, zpart + (int64_t)g * L.zpart_stride,
+              k_out ? k_out + (int64_t)g * kUQ * N : nullptr, rpb, (int)L.npad, (int*)nullptr, z + g * kUQ, kmax + g * kUQ,
+              sparse ? lists.dense : (int*)nullptr);
     SDN_LAUNCHED();
   }
   for (int g = 0; g < G && !fuse_weights; ++g) {
-    k_umma_zreduce<<<(unsigned)group_rows(g), 256, 0, st>>>(zpart + (int64_t)g * L.zpart_stride, (int)(L.npad / kWRows),
-                                                           z + g * kUQ, kmax + g * kUQ, sparse ? lists.dense : nullptr);
+    launch_ex(k_umma_zreduce, dim3((unsigned)group_rows(g)), dim3(256), 0, st, pdl,
+              (const float*)(zpart + (int64_t)g * L.zpart_stride), (int)(L.npad / kWRows), z + g * kUQ, kmax + g * kUQ,
+              sparse ? lists.dense : (int*)nullptr);
     SDN_LAUNCHED();
   }
   if (sparse) {
@@ -1453,6 +1503,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   al.flags = sparse ? lists.flags : nullptr; al.count = sparse ? lists.count : nullptr;
   al.dense = sparse ? lists.dense : nullptr; al.e = e;
   al.gridx = nsplit == 1 ? std::min(dblocks, kNumSMs) : dblocks;
+  al.pdl = pdl;
   // chains longer than kBChunk row blocks are split over the two TMEM accumulators (fp32 register drain)
   al.chunked = (rblocks + nsplit - 1) / nsplit > kBChunk;
   if (G == 1) launch_accum<1>(al, st); else launch_accum<2>(al, st);

@@ -1,4 +1,8 @@
-echo "fat tiles lag1"; timeout 200 python tools/gpu_stream_probe2.py 2>&1 | tail -6
-echo lag2; SDN_STREAM_LAG=2 timeout 200 python tools/gpu_stream_probe2.py 2>&1 | tail -6
-echo lag3; SDN_STREAM_LAG=3 timeout 200 python tools/gpu_stream_probe2.py 2>&1 | tail -6
-echo lag2 q8tn4; SDN_STREAM_LAG=2 SDN_STREAM_Q8_TN4=1 timeout 200 python tools/gpu_stream_probe2.py 2>&1 | tail -2 | head -1
+echo pdl=1; timeout 120 python tools/gpu_umma_l2keep.py 64 3000 2>&1 | tail -1
+echo pdl=0; SDN_PDL=0 timeout 120 python tools/gpu_umma_l2keep.py 64 3000 2>&1 | tail -1
+echo pdl=1; timeout 120 python tools/gpu_umma_l2keep.py 64 375 2>&1 | tail -1
+echo pdl=0; SDN_PDL=0 timeout 120 python tools/gpu_umma_l2keep.py 64 375 2>&1 | tail -1
+echo pdl=1; timeout 120 python tools/gpu_umma_l2keep.py 128 30000 2>&1 | tail -1
+echo pdl=1; timeout 120 python tools/gpu_umma_l2keep.py 16 515 2>&1 | tail -1
+echo pdl=0; SDN_PDL=0 timeout 120 python tools/gpu_umma_l2keep.py 16 515 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
