@@ -247,6 +247,9 @@ int sdn_shard_merge_correct(const void* const* peer_packed, void* const* peer_ou
  * wsum_out [Q] = sum_i relu(radius/d_qi - 1)  (is_negation = wsum != 0, threshold.py:447-450).
  * xq (may be NULL = x0_inout) is the query the distances and the force are taken on; fast_sdv3.py:332 takes them on
  * the channel-normalised query while the update still lands on the un-normalised x0.  xsq = ||xq||^2.
+ * Q <= 8 on a shape the one-pass cluster kernel supports, and workspace >= sdn_repel_workspace_bytes(Q, N, D,
+ * SDN_PATH_STREAM) + Q*D*4 (+ 512): the bank is read ONCE (SPELL weight as a functor of k_stream); otherwise the
+ * generic two-pass kernels run (workspace >= Q*N*4 + Q*D*4 + 512).
  */
 int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t D,
                      float* x0_inout, const float* xq, const float* xsq, int64_t Q,
@@ -262,6 +265,12 @@ int sdn_sparse_partial(const float* bank, const float* sqnorm, int64_t N, int64_
                        float* num_out, float* wsum_out, void* workspace, size_t workspace_bytes, void* stream);
 int sdn_sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale,
                      const float* xq, float* x0_inout, float* term_out, void* stream);
+/* sdn_sparse_partial for batched queries on the tcgen05 kernels (the bf16 hi/lo planes of sdn_bank_prepare instead of
+ * the fp32 bank): the SPELL weight replaces the Gaussian one in the weights step between the two contractions.
+ * workspace >= sdn_repel_workspace_bytes(Q, N, D, SDN_PATH_UMMA).  Follow with sdn_sparse_apply. */
+int sdn_sparse_partial_planes(const void* planes, const float* sqnorm, int64_t N, int64_t D,
+                              const float* xq, const float* xsq, int64_t Q, float radius,
+                              float* num_out, float* wsum_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- host-buffer convenience: the e2e path ------------------------------------------------
  * One conditioning() call with HOST tensors: H2D of x0_host [Q,D], projection over a device-resident

@@ -46,6 +46,7 @@ SIGNATURES = {
     "sdn_sparse_repel": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _f, _f, _p, _p, _p, _sz, _p]),
     "sdn_sparse_partial": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _f, _p, _p, _p, _sz, _p]),
     "sdn_sparse_apply": (C.c_int, [_p, _p, _i64, _i64, _f, _p, _p, _p, _p]),
+    "sdn_sparse_partial_planes": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _f, _p, _p, _p, _sz, _p]),
     "sdn_conditioning_host": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _i32, _f, _i32, _f, _f, _f,
                                         _p, _i32, _p]),
     "sdn_host_release": (None, []),

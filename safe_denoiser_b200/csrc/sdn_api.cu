@@ -212,6 +212,18 @@ int sdn_sparse_repel(const float* bank, const float* sqnorm, int64_t N, int64_t 
   float* num = reinterpret_cast<float*>(static_cast<char*>(workspace) + s_bytes);
   const float* query = xq ? xq : x0_inout;
   if (!aligned16(query)) return SDN_E_ALIGN;
+  // Q <= 8 on a shape the one-pass cluster kernel takes: the SPELL weight is one more functor of k_stream -- the bank
+  // is read once (the generic kernels below read it twice and keep a [Q,N] scratch)
+  {
+    const size_t sws = align_up(stream_workspace_bytes(Q, N, D), 256);
+    if (stream_supported(Q, N, D) && workspace_bytes >= sws + align_up(sizeof(float) * Q * D, 256)) {
+      float* num2 = reinterpret_cast<float*>(static_cast<char*>(workspace) + sws);
+      const int rc2 = stream_partial(bank, sqnorm, N, D, query, xsq, Q, radius, kPowerSparse, 1.f, num2, wsum_out, nullptr,
+                                     workspace, sws, st);
+      if (rc2) return rc2;
+      return sparse_apply(num2, wsum_out, Q, D, scale, query, x0_inout, term_out, st);
+    }
+  }
   int rc = generic_dots(bank, N, D, query, Q, S, st);
   if (rc) return rc;
   rc = sparse_weights(S, sqnorm, xsq, Q, N, radius, wsum_out, st);
@@ -227,14 +239,29 @@ int sdn_sparse_partial(const float* bank, const float* sqnorm, int64_t N, int64_
   if (!bank || !sqnorm || !xq || !xsq || !num_out || !wsum_out || !workspace) return SDN_E_NULL;
   if (Q <= 0 || N <= 0 || D <= 0 || Q > 65535) return SDN_E_SHAPE;
   if (D % 4 != 0 || !aligned16(bank) || !aligned16(xq) || !aligned16(num_out)) return SDN_E_ALIGN;
-  if (workspace_bytes < generic_workspace_bytes(Q, N)) return SDN_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  if (stream_supported(Q, N, D) && workspace_bytes >= stream_workspace_bytes(Q, N, D))
+    return stream_partial(bank, sqnorm, N, D, xq, xsq, Q, radius, kPowerSparse, 1.f, num_out, wsum_out, nullptr, workspace,
+                          workspace_bytes, st);
+  if (workspace_bytes < generic_workspace_bytes(Q, N)) return SDN_E_WORKSPACE;
   float* S = static_cast<float*>(workspace);
   int rc = generic_dots(bank, N, D, xq, Q, S, st);
   if (rc) return rc;
   rc = sparse_weights(S, sqnorm, xsq, Q, N, radius, wsum_out, st);
   if (rc) return rc;
   return generic_accum(bank, N, D, S, Q, num_out, st);
+}
+
+int sdn_sparse_partial_planes(const void* planes, const float* sqnorm, int64_t N, int64_t D, const float* xq,
+                              const float* xsq, int64_t Q, float radius, float* num_out, float* wsum_out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (!planes || !sqnorm || !xq || !xsq || !num_out || !wsum_out || !workspace) return SDN_E_NULL;
+  if (Q <= 0 || N <= 0 || D <= 0 || Q > 65535) return SDN_E_SHAPE;
+  if (D % 4 != 0 || !aligned16(xq) || !aligned16(num_out)) return SDN_E_ALIGN;
+  if (!umma_supported(Q, N, D, planes)) return SDN_E_UNSUPPORTED;
+  if (workspace_bytes < umma_workspace_bytes(Q, N, D)) return SDN_E_WORKSPACE;
+  return umma_partial(planes, sqnorm, N, D, xq, xsq, Q, radius, kPowerSparse, 1.f, num_out, wsum_out, nullptr, workspace,
+                      workspace_bytes, (cudaStream_t)stream, false);
 }
 
 int sdn_sparse_apply(const float* num, const float* wsum, int64_t Q, int64_t D, float scale, const float* xq,

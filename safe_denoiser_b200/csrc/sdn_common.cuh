@@ -107,4 +107,16 @@ __device__ __forceinline__ float dist_from_dot(float xsq, float nsq, float dot, 
   return power == 1 ? sqrtf(d2) : d2;
 }
 
+// Weight of a bank row for a query: the Gaussian kernel of the projection, or -- internal mode kPowerSparse, reached
+// only through sdn_sparse_* -- the SPELL force weight relu(radius / d - 1) on the un-squared distance d < radius
+// (fast.py:312-326); the radius then travels in the `inv2s2` argument.
+constexpr int kPowerSparse = -1;
+__device__ __forceinline__ float weight_from_dot(float xsq, float nsq, float dot, float alpha, int power, float inv2s2) {
+  if (power == kPowerSparse) {
+    const float d = dist_from_dot(xsq, nsq, dot, alpha, 1);
+    return d < inv2s2 ? fmaxf(inv2s2 / d - 1.f, 0.f) : 0.f;
+  }
+  return expf(-dist_from_dot(xsq, nsq, dot, alpha, power) * inv2s2);
+}
+
 }  // namespace sdn

@@ -268,8 +268,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_stream(const StreamArgs a) {
           float dot = 0.f;
           const float* rs = recv + (size_t)sl * kStMaxCluster * V + lane;
           for (uint32_t src = 0; src < csize; ++src) dot += rs[src * V];
-          const float d = dist_from_dot(xs_q, nsq, dot, a.alpha, a.power);
-          k = expf(-d * a.inv2s2);
+          k = weight_from_dot(xs_q, nsq, dot, a.alpha, a.power, a.inv2s2);
           if (crank == 0 && a.k_out && q < a.q_real) a.k_out[(int64_t)q * a.N + r0 + r] = k;
         }
         ks[sl * V + lane] = k;

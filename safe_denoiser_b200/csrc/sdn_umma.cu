@@ -275,7 +275,7 @@ __device__ __forceinline__ void dots_tail(const DotsTail& T, const float* __rest
           dot += G == 1 ? p[0] + p[kUQ] : p[0];
         }
         float k = 0.f;
-        if (row < T.N && q < Qg) k = expf(-dist_from_dot(xs[g], sq_s[r0 + i], dot, T.alpha, T.power) * T.inv2s2);
+        if (row < T.N && q < Qg) k = weight_from_dot(xs[g], sq_s[r0 + i], dot, T.alpha, T.power, T.inv2s2);
         __nv_bfloat16* Pg = T.P + (int64_t)g * T.p_group_stride;
         const __nv_bfloat16 h = __float2bfloat16_rn(k);
         Pg[(int64_t)row * kUStack + q] = h;
@@ -566,7 +566,7 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
         if (sp0 + u < ksplit) dot += lo_off > 0 ? a[u] + b[u] : a[u];
     }
     float k = 0.f;
-    if (i < N && q < Q) k = expf(-dist_from_dot(xs, sq, dot, alpha, power) * inv2s2);
+    if (i < N && q < Q) k = weight_from_dot(xs, sq, dot, alpha, power, inv2s2);
     const __nv_bfloat16 h = __float2bfloat16_rn(k);
     P[(int64_t)i * kUStack + q] = h;
     P[(int64_t)i * kUStack + kUQ + q] = __float2bfloat16_rn(k - __bfloat162float(h));
@@ -1383,7 +1383,9 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   lists.dense = lists.count + G * kUQ;
   lists.rows = lists.dense + 4;
   lists.ks = reinterpret_cast<float*>(lists.rows + G * kUQ * kListCap);
-  const bool sparse = g_skip_negligible.load(std::memory_order_relaxed) && nflags <= kMaxActive && (num || epi);
+  // (SPELL weights are not exponentially peaked: no significant-row lists in that mode)
+  const bool sparse = g_skip_negligible.load(std::memory_order_relaxed) && nflags <= kMaxActive && (num || epi) &&
+                      power != kPowerSparse;
   float* zpart = reinterpret_cast<float*>(w + L.off_z);
   float* xsq_part = reinterpret_cast<float*>(w + L.off_q);
   auto group_rows = [&](int g) { return (int)std::min<int64_t>(kUQ, Q - (int64_t)g * kUQ); };

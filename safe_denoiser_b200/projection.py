@@ -436,9 +436,24 @@ class Projector:
         xq = s.xq if normalize_channels > 0 else None
         nv.check(L.sdn_query_prepare(nv.ptr(xf), None, 1.0, 0.0, Q, b.D, int(normalize_channels), None, nv.ptr(xq),
                                      nv.ptr(s.xsq), st))
-        need = Q * b.N * 4 + Q * b.D * 4 + 1024
+        # generic kernels: [Q,N] scratch + [Q,D]; the one-pass (Q <= 8) and tcgen05 (batched) kernels: their workspace + [Q,D]
+        need = max(Q * b.N * 4, int(L.sdn_repel_workspace_bytes(Q, b.N, b.D, nv.PATH_AUTO))) + Q * b.D * 4 + 1024
         ws = torch.empty(need, dtype=torch.uint8, device=b.device)
         term = torch.empty_like(xf) if want_term else None
+        query = xq if xq is not None else xf
+        batched = Q > 8 and b.D % 128 == 0
+        if batched:
+            b.ensure_planes()
+            # SPELL on the tcgen05 two-phase kernels (weights step with the relu(radius/d - 1) functor)
+            packed = torch.empty(Q * b.D + Q, dtype=torch.float32, device=b.device)
+            num, wsum = packed[: Q * b.D].view(Q, b.D), packed[Q * b.D:]
+            nv.check(L.sdn_sparse_partial_planes(nv.ptr(b.planes), nv.ptr(b.sqnorm), b.N, b.D, nv.ptr(query), nv.ptr(s.xsq), Q,
+                                                 float(radius), nv.ptr(num), nv.ptr(wsum), nv.ptr(ws), need, st))
+            if self.group is not None:
+                merge_partials(packed, self.group)
+            nv.check(L.sdn_sparse_apply(nv.ptr(num), nv.ptr(wsum), Q, b.D, float(scale), nv.ptr(query), nv.ptr(xf),
+                                        nv.ptr(term), st))
+            return term, wsum
         if self.group is None:
             wsum = torch.empty(Q, dtype=torch.float32, device=b.device)
             nv.check(L.sdn_sparse_repel(nv.ptr(b.flat), nv.ptr(b.sqnorm), b.N, b.D, nv.ptr(xf), nv.ptr(xq), nv.ptr(s.xsq), Q,

@@ -530,3 +530,29 @@ def test_cfg5_size_properties(nv):
     Projector(NegativeBank(bank4)).partial_sums(xq, 1.0, k_out=k)
     torch.cuda.synchronize()
     assert int(k.argmax()) == 123 and float(k.max()) > 0.9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Q,N,H", [(1, 515, 64), (2, 300, 64), (6, 130, 64), (16, 515, 64), (70, 257, 64), (3, 40, 8)])
+def test_spell_on_the_fast_kernels_matches_the_oracle(nv, Q, N, H):
+    """SPELL (fast.py:306-340) as a weight functor of the one-pass cluster kernel (Q <= 8: the bank is read once) and of
+    the tcgen05 weights step (batched), against the float64 restatement; the last shape takes the generic kernels.
+    The radius sits inside the spread of the query-to-bank distances, so the set of neighbours is a proper subset."""
+    from oracle import repellency_oracle as orc
+    from safe_denoiser_b200.projection import NegativeBank, Projector
+    bank4 = orc.synthetic_bank(N, 4, H, H)
+    x4 = orc.synthetic_queries(bank4, Q, "mid")
+    bf = bank4.reshape(N, -1).numpy().astype(np.float64)
+    d = np.stack([np.sqrt(((xq[None, :] - bf) ** 2).sum(1)) for xq in x4.reshape(Q, -1).numpy().astype(np.float64)], 0)
+    radius = float(np.quantile(d, 0.3))
+    want = orc.sparse_repellency(x4.numpy(), bank4.numpy(), radius, scale=0.7)
+    assert 0 < (want["trunc_weight"] > 0).sum() < Q * N
+    proj = Projector(NegativeBank(bank4.cuda(), with_planes=False))
+    x = x4.cuda()
+    c0 = nv.launch_count()
+    term, wsum = proj.sparse(x, radius, 0.7, want_term=True)
+    torch.cuda.synchronize()
+    assert nv.launch_count() - c0 <= (6 if Q <= 8 else 12)    # batched: + the plane build and the tcgen05 chain (two query groups: 11)
+    assert rel(x.reshape(Q, -1), want["x_0_hat"].reshape(Q, -1)) <= TOL
+    assert rel(term.reshape(Q, -1), want["term"].reshape(Q, -1)) <= TOL
+    assert rel(wsum, want["trunc_weight"].sum(1)) <= TOL
