@@ -419,9 +419,20 @@ def main():
         # the ranks leave the host barrier some 100 us apart; a device-side rendezvous (one tiny all-reduce, enqueued
         # and not waited for) lines the GPU timelines up, otherwise the first timed step measures that host skew
         dist.all_reduce(torch.zeros(1, device=dev))
+    sync_word = torch.zeros(1, device=dev)
+    # a few untimed flushes first: ~1 ms of queued GPU work lets the host run ahead, otherwise step 0 measures the
+    # host enqueueing its launch (the GPU has caught up with the host right after the barrier)
+    for _ in range(4):
+        flush_l2()
     for i in range(args.steps):
         x.copy_(x_src)
         flush_l2()
+        if world > 1:
+            # the L2 flush (512 MiB of traffic, outside the step's events) does not take the same time on every GPU:
+            # without a rendezvous the rank that finishes it first starts its step early and then sits in the merge
+            # kernel waiting for the others, and that wait would be billed to the step.  One tiny all-reduce, enqueued
+            # and not waited for by the host, lines the GPU timelines up before the start event of every step.
+            dist.all_reduce(sync_word)
         ev0[i].record()
         step()
         ev1[i].record()
@@ -431,7 +442,9 @@ def main():
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in zip(ev0, ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
-    step_sorted = sorted(step_ms.tolist())
+    step_list = step_ms.tolist()
+    slowest_step = int(max(range(len(step_list)), key=lambda j: step_list[j]))
+    step_sorted = sorted(step_list)
     total_ms = float(step_ms.sum().item())
     ms_per_step = total_ms / args.steps
     value = Q * args.steps / (total_ms * 1e-3)
@@ -610,7 +623,9 @@ def main():
         line = dict(base)
         line["config"] = dict(base["config"],
                               l2="flushed between steps outside the per-step events: 256 MiB memset, then a 256 MiB read so that no dirty lines are left",
-                              timing="per-step CUDA-event intervals, max over ranks per step, summed",
+                              timing="per-step CUDA-event intervals, max over ranks per step, summed"
+                              + ("; at N > 1 a one-element all-reduce before every step's start event aligns the ranks "
+                                 "(the L2 flush outside the events takes a different time on every GPU)" if world > 1 else ""),
                               kernel_path=args.path,
                               accumulate_pass="block-sparse (rows below fp32 resolution skipped)" if args.sparse
                               else "dense (every bank row read; the library default would skip negligible rows)",
@@ -623,7 +638,8 @@ def main():
                               if world > 1 else None)
         line.update({
             "value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
-            "step_ms": {"p50": pct(0.5), "p95": pct(0.95), "max": step_sorted[-1], "min": step_sorted[0]},
+            "step_ms": {"p50": pct(0.5), "p95": pct(0.95), "max": step_sorted[-1], "min": step_sorted[0],
+                        "slowest_step_index": slowest_step},
             "e2e": {"value": e2e_value, "unit": "projections/s", "h2d_bytes_per_step": Q * D * 4,
                     "d2h_bytes_per_step": Q * D * 4 + Q * 4, "steps": e2e_steps},
             "parity_check": parity,

@@ -63,9 +63,11 @@ constexpr int kFJobs = kFR / kFJobRows; // 32 jobs per tile, two work units (hal
 constexpr int kFUnits = kFJobs * 2;     // counter increments per tile
 constexpr int kFRingL = 16;             // slots of the level-1 partial ring (2 MiB each)
 constexpr int kFRingP = 32;             // slots of the weight / z-partial / counter rings
-constexpr int kFWindow = 8;             // tiles between the two reads of the bank: 8 x 8 MiB stay in the 126 MB L2 (6: 132 us, 8: 116 us, 12: 114 us at cfg3); also what
-                                        // makes ring reuse safe (2 window + 6 <= kFRingP, window <= kFRingL, window < 8 tiles
-                                        // between two units of a level-2 worker)
+constexpr int kFWindow = 6;             // tiles between the two reads of the bank: 6 x 8 MiB stay in the 126 MB L2.  Measured at
+                                        // cfg3 (ncu dram__bytes_read, profiles/r02_flash2_cfg3_window_dram.csv): window 6 -> 234.9 MB
+                                        // (1.15 x the algorithmic 205 MB), 7 -> 255.7 MB, 8 -> 281.1 MB (the second read starts to miss)
+                                        // while the step goes 132 -> 116 us (SDN_FLASH_WINDOW, <= 13).  Also what makes ring reuse
+                                        // safe (2 window + 6 <= kFRingP, window <= kFRingL)
 constexpr int kFThreads = 512;
 constexpr int kFMaxCtas = 128;
 constexpr int kFMaxGroups = kFMaxCtas / kFGS;

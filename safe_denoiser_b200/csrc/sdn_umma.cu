@@ -501,25 +501,27 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 constexpr int kWRows = 4;          // bank rows a block handles per step (and per k_umma_siglist block)
 
 // The dot of query row q is S_T[..][col0 + q] (+ S_T[..][col0 + lo_off + q] when lo_off > 0: stacked operand).
-__global__ void __launch_bounds__(kWRows * kUQ)
+constexpr int kWMaxLanes = 16;     // row lanes of the fat-block variant (1024 threads)
+__global__ void __launch_bounds__(kWMaxLanes * kUQ)
 k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, int col0, int lo_off,
                const float* __restrict__ sqnorm,
                const float* __restrict__ xsq, const float* __restrict__ xsq_part, int xsq_nparts, int N, int Q,
                float inv2s2, int power, float alpha, __nv_bfloat16* __restrict__ P, float* __restrict__ zpart,
                float* __restrict__ k_out, int rows_per_block, int npad, int* __restrict__ arrivals, float* __restrict__ z,
                float* __restrict__ kmax, int* __restrict__ dense_flag) {
-  __shared__ float zs[kWRows][kUQ], zm[kWRows][kUQ];
+  __shared__ float zs[kWMaxLanes][kUQ], zm[kWMaxLanes][kUQ];
   __shared__ int s_last;
   pdl_launch_dependents();
   pdl_wait();
   const int q = threadIdx.x & (kUQ - 1);
   const int rsub = threadIdx.x >> 6;
+  const int lanes = (int)blockDim.x >> 6;           // bank rows the block handles per step
   float zsum = 0.f, zmax = 0.f;
   const int i0 = blockIdx.x * rows_per_block;
   float xs = 0.f;
   bool have_xs = false;
 #pragma unroll 1
-  for (int r = rsub; r < rows_per_block && i0 + r < npad; r += kWRows) {
+  for (int r = rsub; r < rows_per_block && i0 + r < npad; r += lanes) {
     const int i = i0 + r;
     // every load of the row is issued before the first use: the kernel is one L2 round trip deep, not three
     const float* s = S_T + (int64_t)i * kUStack + col0 + q;
@@ -578,15 +580,14 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
   __syncthreads();
   if (threadIdx.x < kUQ) {
     float t = 0.f, m = 0.f;
-#pragma unroll
-    for (int r = 0; r < kWRows; ++r) {
+    for (int r = 0; r < lanes; ++r) {
       t += zs[r][threadIdx.x];
       m = fmaxf(m, zm[r][threadIdx.x]);
     }
     zpart[(int64_t)blockIdx.x * kUStack + threadIdx.x] = t;          // [block][0..63]  sums
     zpart[(int64_t)blockIdx.x * kUStack + kUQ + threadIdx.x] = m;    // [block][64..127] maxima
   }
-  if (!arrivals) return;               // k_umma_zreduce sums the partials
+  if (!arrivals) return;               // k_umma_zreduce (or phase B's epilogue warps) sums the partials
   // ---- the last block sums the partials in block order (deterministic)
   __threadfence();
   __syncthreads();
@@ -595,11 +596,11 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
   if (!s_last) return;
   __threadfence();
   float a = 0.f, m = 0.f;
-  for (int b0 = rsub; b0 < (int)gridDim.x; b0 += 8 * kWRows) {
+  for (int b0 = rsub; b0 < (int)gridDim.x; b0 += 8 * lanes) {
     float va[8], vm[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int b = b0 + u * kWRows;
+      const int b = b0 + u * lanes;
       va[u] = b < (int)gridDim.x ? __ldcg(zpart + (int64_t)b * kUStack + q) : 0.f;
       vm[u] = b < (int)gridDim.x ? __ldcg(zpart + (int64_t)b * kUStack + kUQ + q) : 0.f;
     }
@@ -611,8 +612,7 @@ k_umma_weights(const float* __restrict__ S_T, int64_t split_stride, int ksplit, 
   __syncthreads();
   if (threadIdx.x < kUQ && threadIdx.x < Q) {
     float t = 0.f, mm = 0.f;
-#pragma unroll
-    for (int r = 0; r < kWRows; ++r) { t += zs[r][threadIdx.x]; mm = fmaxf(mm, zm[r][threadIdx.x]); }
+    for (int r = 0; r < lanes; ++r) { t += zs[r][threadIdx.x]; mm = fmaxf(mm, zm[r][threadIdx.x]); }
     z[threadIdx.x] = t;
     kmax[threadIdx.x] = mm;
     // sum_i k_i / kmax <= (#rows with k_i >= tau kmax) + N tau: more than kListCap "effective rows" means the
@@ -778,6 +778,10 @@ struct AccumEpi {
   float eps, scale, gate_thr; int flags;
   float* x0; float* neg_out; float* denom_out; int32_t* gate_out; float* mean_out; float inv_qd;
   int reverse;          // walk the row blocks from the last to the first (the rows phase A read last are still in L2)
+  // z from the weights kernel's per-block partials [nzpart][128] (group g at + g * zpart_stride), summed in block order
+  // by this kernel's epilogue warps while the main loop runs -- instead of a k_umma_zreduce launch (6 us at cfg3).  The
+  // CTAs of d-block 0 also write the sums to `z` (which then is an output).  Null: read z.
+  const float* zpart; int nzpart; int64_t zpart_stride; float* z_out;
 };
 
 // grid (D / 128, n splits).  num[q][d] (+)= sum_i P[q][i] * (hi+lo)[i][d] over this split's bank rows, for the
@@ -799,6 +803,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint16_t act[kMaxActive];
   __shared__ int nact_s;
+  __shared__ float z_half[G][2][kUQ], z_sum[G][kUQ];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb0 = (int)((int64_t)blockIdx.y * rblocks_total / nsplit);
@@ -941,7 +946,30 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     const int64_t qoff = (int64_t)g * kUQ * D;
     // bank-row splits write their own partial [Q][D] (summed in split order by k_umma_splitsum): no atomics
     float* const numg = num ? num + qoff + (int64_t)blockIdx.y * split_stride : nullptr;
-    const float* const zg = epi.z ? epi.z + g * kUQ : nullptr;
+    // z of this group: from global memory (made by k_umma_zreduce), or summed here from the weights kernel's partials
+    const float* zg = epi.z ? epi.z + g * kUQ : nullptr;
+    if (epi.zpart) {
+      const int t = (warp - 2 - 4 * g) * 32 + lane;          // 0..127 within the group's four warps
+      const int qz = t & (kUQ - 1), half = t >> 6;
+      const float* zp = epi.zpart + (int64_t)g * epi.zpart_stride + qz;
+      float a = 0.f;
+      for (int b0 = half; b0 < epi.nzpart; b0 += 16) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = b0 + 2 * u < epi.nzpart ? __ldcg(zp + (int64_t)(b0 + 2 * u) * kUStack) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a += v[u];
+      }
+      z_half[g][half][qz] = a;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      if (t < kUQ) {
+        const float zz = z_half[g][0][t] + z_half[g][1][t];
+        z_sum[g][t] = zz;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && epi.z_out && t < Qg) epi.z_out[g * kUQ + t] = zz;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      zg = z_sum[g];
+    }
     float* const x0g = epi.x0 ? epi.x0 + qoff : nullptr;
     float* const negg = epi.neg_out ? epi.neg_out + qoff : nullptr;
     float* const denomg = epi.denom_out ? epi.denom_out + g * kUQ : nullptr;
@@ -976,7 +1004,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int q = min(c * 32 + j, Qg - 1);
-          dn[j] = __ldg(zg + q) + epi.eps;
+          dn[j] = zg[q] + epi.eps;
           xv[j] = x0g ? __ldcg(x0g + (int64_t)q * D + d) : 0.f;
         }
 #pragma unroll
@@ -1050,7 +1078,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int q = min(cq * 32 + j, Qg - 1);
-            dn[j] = __ldg(zg + q) + epi.eps;
+            dn[j] = zg[q] + epi.eps;
             xv[j] = x0g ? __ldcg(x0g + (int64_t)q * D + d) : 0.f;
           }
 #pragma unroll
@@ -1448,12 +1476,18 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   SDN_LAUNCHED();
 
   // weights, z, lists: per group (unless the fused step is on)
+  // single GPU, dense accumulate, correction fused into phase B: z is summed by phase B's idle epilogue warps from this
+  // kernel's partials -- no k_umma_zreduce launch (SDN_UMMA_ZREDUCE=1 keeps it)
+  static const bool keep_zreduce = [] { const char* e = getenv("SDN_UMMA_ZREDUCE"); return e && atoi(e) != 0; }();
+  const bool fuse_z = epi != nullptr && !sparse && !fuse_weights && !keep_zreduce;
+  const int fuse_z_rpb = (L.npad >= 3072 ? 2 : 1) * kWMaxLanes;      // small banks: one row per thread (more blocks)
   pid = g_prof.begin(fuse_weights ? "k_umma_siglist" : "k_umma_weights", st);
   for (int g = 0; g < G && !fuse_weights; ++g) {
-    // one bank row per thread: few fat blocks (rows in a loop, last block sums z) measured slower -- 8 warps per SM do
-    // not hide the L2 latency of the partial loads (14.7 us at cfg3 against 5 + 4 us for this kernel + k_umma_zreduce)
-    const int rpb = kWRows;
-    launch_ex(k_umma_weights, dim3((unsigned)cdiv(L.npad, rpb)), dim3(kWRows * kUQ), 0, st, pdl,
+    // one bank row per thread and step: few fat blocks (many rows in a loop, last block sums z) measured slower -- 8
+    // warps per SM do not hide the L2 latency of the partial loads (14.7 us at cfg3 against 5 + 4 us for this kernel +
+    // k_umma_zreduce).  fuse_z: 1024-thread blocks of 32 rows, so that phase B's epilogue warps have few partials to sum
+    const int rpb = fuse_z ? fuse_z_rpb : kWRows;
+    launch_ex(k_umma_weights, dim3((unsigned)cdiv(L.npad, rpb)), dim3((fuse_z ? kWMaxLanes : kWRows) * kUQ), 0, st, pdl,
               (const float*)S_T, L.split_stride, L.ksplit, g * kUQ, G == 1 ? kUQ : 0, sqnorm, xsq ? xsq + g * kUQ : nullptr,
               (const float*)(xsq_part + (int64_t)g * L.xsq_nparts * kUQ), L.xsq_nparts, (int)N, group_rows(g), inv2s2, power,
               alpha, P + (int64_t)g * L.npad * kUStack, zpart + (int64_t)g * L.zpart_stride,
@@ -1461,7 +1495,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
               sparse ? lists.dense : (int*)nullptr);
     SDN_LAUNCHED();
   }
-  for (int g = 0; g < G && !fuse_weights; ++g) {
+  for (int g = 0; g < G && !fuse_weights && !fuse_z; ++g) {
     launch_ex(k_umma_zreduce, dim3((unsigned)group_rows(g)), dim3(256), 0, st, pdl,
               (const float*)(zpart + (int64_t)g * L.zpart_stride), (int)(L.npad / kWRows), z + g * kUQ, kmax + g * kUQ,
               sparse ? lists.dense : (int*)nullptr);
@@ -1489,6 +1523,9 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     e = *epi;
   }
   e.reverse = l2keep ? 1 : 0;
+  if (fuse_z) {
+    e.zpart = zpart; e.nzpart = (int)cdiv(L.npad, fuse_z_rpb); e.zpart_stride = L.zpart_stride; e.z_out = z;
+  }
   float* const part = reinterpret_cast<float*>(w + L.off_n);
   if (sparse) {
     pid = g_prof.begin("k_umma_listed_accum", st);

@@ -420,7 +420,9 @@ def test_block_sparse_accumulate_equals_dense(nv, regime, sigma, nq):
         assert rel(out[on]["weights"], want["weights"]) <= TOL
     nv.set_option(nv.OPT_SKIP_NEGLIGIBLE, 1)
     assert rel(out[1]["num"], out[0]["num"]) <= 1e-5
-    assert rel(out[1]["denom"], out[0]["denom"]) == 0.0
+    # z: k_umma_zreduce (block-sparse mode) and phase B's epilogue warps (dense mode) sum the same per-block partials in
+    # different fixed orders
+    assert rel(out[1]["denom"], out[0]["denom"]) <= 1e-6
 
 
 @pytest.mark.parametrize("nq", [24, 72])
