@@ -782,6 +782,7 @@ struct AccumEpi {
   // by this kernel's epilogue warps while the main loop runs -- instead of a k_umma_zreduce launch (6 us at cfg3).  The
   // CTAs of d-block 0 also write the sums to `z` (which then is an output).  Null: read z.
   const float* zpart; int nzpart; int64_t zpart_stride; float* z_out;
+  int z_only;           // zpart given but no correction here (N-sharded banks: the merge kernel applies it): write z_out only
 };
 
 // grid (D / 128, n splits).  num[q][d] (+)= sum_i P[q][i] * (hi+lo)[i][d] over this split's bank rows, for the
@@ -968,7 +969,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         if (blockIdx.x == 0 && blockIdx.y == 0 && epi.z_out && t < Qg) epi.z_out[g * kUQ + t] = zz;
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-      zg = z_sum[g];
+      zg = epi.z_only ? nullptr : z_sum[g];
     }
     float* const x0g = epi.x0 ? epi.x0 + qoff : nullptr;
     float* const negg = epi.neg_out ? epi.neg_out + qoff : nullptr;
@@ -1479,7 +1480,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   // single GPU, dense accumulate, correction fused into phase B: z is summed by phase B's idle epilogue warps from this
   // kernel's partials -- no k_umma_zreduce launch (SDN_UMMA_ZREDUCE=1 keeps it)
   static const bool keep_zreduce = [] { const char* e = getenv("SDN_UMMA_ZREDUCE"); return e && atoi(e) != 0; }();
-  const bool fuse_z = epi != nullptr && !sparse && !fuse_weights && !keep_zreduce;
+  const bool fuse_z = (epi != nullptr || (num != nullptr && L.nsplit == 1)) && !sparse && !fuse_weights && !keep_zreduce;
   const int fuse_z_rpb = (L.npad >= 3072 ? 2 : 1) * kWMaxLanes;      // small banks: one row per thread (more blocks)
   pid = g_prof.begin(fuse_weights ? "k_umma_siglist" : "k_umma_weights", st);
   for (int g = 0; g < G && !fuse_weights; ++g) {
@@ -1525,6 +1526,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   e.reverse = l2keep ? 1 : 0;
   if (fuse_z) {
     e.zpart = zpart; e.nzpart = (int)cdiv(L.npad, fuse_z_rpb); e.zpart_stride = L.zpart_stride; e.z_out = z;
+    e.z_only = epi ? 0 : 1;
   }
   float* const part = reinterpret_cast<float*>(w + L.off_n);
   if (sparse) {
