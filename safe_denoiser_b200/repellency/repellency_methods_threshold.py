@@ -50,6 +50,9 @@ class RepellencyMethod(RepellencyBase):
         self.beta_threshold_margin = kwargs.get('beta_threshold_margin', 0.0)
         self.proj_beta_ref_path = kwargs.get('proj_noisy_ref_path_for_beta', None)
         self.cache_proj_beta_ref = kwargs.get('cache_noisy_ref_path_for_beta', False)
+        # not a reference kwarg: calibrate beta without materialising the {t: noisy bank} dictionary (50 N D floats,
+        # 9.8 GB at N = 3000) and without writing its cache file -- see empirical_beta_streaming
+        self.stream_beta_calibration = kwargs.get('stream_beta_calibration', False)
 
     # ---- noisy bank for the calibration (threshold.py:108-155) ---------------------------------
     def set_noisy_proj_ref(self, scheduler, num_timesteps=None, **kwargs):
@@ -146,6 +149,12 @@ class RBFKernelRepellency(_Calibrated):
         super().__init__(ref_data, embed_fn, forward_fn, num_timesteps, max_idx, beta_min, beta_max, **kwargs)
         self.scale = kwargs.get('scale', 1.0)
         self.beta_threshold = kwargs.get('beta_threshold', -1.0)
+        if self.beta_threshold <= 0 and self.stream_beta_calibration and not self.cache_proj_beta_ref:
+            scheduler = kwargs.get("scheduler", None)
+            assert scheduler != None, "We need scheduler for computing \\beta reference"  # noqa: E711
+            betas = self.empirical_beta_streaming(scheduler, sigma=self.sigma, quantitle=self.quantile,
+                                                  **{k: kwargs[k] for k in ("device", "generator") if k in kwargs})
+            self.beta_threshold = float(betas[list(betas.keys())[-1]])
         if self.beta_threshold <= 0:                      # threshold.py:291-306
             self.noisy_proj_refs = self._noisy_refs(kwargs)
             self.noisy_refs_beta_quantitle = self.empirical_beta(sigma=self.sigma, quantitle=self.quantile)
@@ -183,6 +192,39 @@ class RBFKernelRepellency(_Calibrated):
             q1 = torch.quantile(beta, quantitle)
             print(f"Top {100*(1-quantitle):.1f} % of radius at t={t}: {q1.item():.3f}")
             out[t] = q1
+        return out
+
+
+    def empirical_beta_streaming(self, scheduler, sigma=1.0, quantitle=0.25, num_timesteps=None, **kwargs):
+        """set_noisy_proj_ref + empirical_beta (threshold.py:108-155, :351-384) in one sweep that never holds more than
+        one chunk of noisy rows: per timestep, per chunk of n_embed bank rows -- the SAME order in which the reference
+        draws from its generator, so every noise value, every beta_j and every quantile is the one the two-step path
+        produces -- add_noise, then the z-only projection of the chunk (distance kernel + weights, no phase B), and the
+        chunk is dropped.  Memory: n_embed x D instead of 50 x N x D; no cache file is written."""
+        steps = num_timesteps if num_timesteps is not None else (self.num_timesteps or 50)
+        device = kwargs.get("device", "cuda")
+        generator = kwargs.get("generator", None)
+        if generator is None:
+            generator = torch.Generator(device=device).manual_seed(42)
+        bank = self.proj_refs
+        proj = self.projector()
+        scheduler.set_timesteps(steps, device=device)
+        print("*" * 10, "Set Beta Thresholds", "*" * 10)
+        out = {}
+        with torch.no_grad():
+            for t in scheduler.timesteps:
+                print(f"[Empirical Betas] Computing empirical beta for {t.item()}-th step")
+                betas = []
+                for lo in range(0, len(bank), self.n_embed):
+                    clean = bank[lo:lo + self.n_embed]
+                    noise = torch.randn(clean.shape, generator=generator, device=device, dtype=torch.float32)
+                    lat, _ = self._as_query(scheduler.add_noise(clean, noise, t).to(proj.bank.device))
+                    for r0 in range(0, lat.shape[0], 128):
+                        betas.append(proj.partial_sums(lat[r0:r0 + 128], sigma, z_only=True).z.clone())
+                beta = torch.cat(betas) + self.epsilon
+                q1 = torch.quantile(beta, quantitle)
+                print(f"Top {100*(1-quantitle):.1f} % of radius at t={t.item()}: {q1.item():.3f}")
+                out[t.item()] = q1
         return out
 
 

@@ -558,3 +558,38 @@ def test_spell_on_the_fast_kernels_matches_the_oracle(nv, Q, N, H):
     assert rel(x.reshape(Q, -1), want["x_0_hat"].reshape(Q, -1)) <= TOL
     assert rel(term.reshape(Q, -1), want["term"].reshape(Q, -1)) <= TOL
     assert rel(wsum, want["trunc_weight"].sum(1)) <= TOL
+
+
+class _TinyScheduler:
+    """What set_noisy_proj_ref needs of a diffusers scheduler: set_timesteps / timesteps / add_noise (DDPM forward noise
+    with the SD-1.4 schedule of oracle.scheduler_oracle)."""
+
+    def __init__(self):
+        from oracle import scheduler_oracle as so
+        self.ab = torch.tensor(so.sd14_alphas_cumprod(), dtype=torch.float32)
+        self.timesteps = None
+
+    def set_timesteps(self, n, device="cuda"):
+        from oracle import scheduler_oracle as so
+        self.timesteps = torch.tensor([int(t) for t in so.ddpm_timesteps(n)], device=device)
+
+    def add_noise(self, clean, noise, t):
+        ab = self.ab.to(clean.device)[int(t)]
+        return ab.sqrt() * clean + (1.0 - ab).sqrt() * noise
+
+
+@pytest.mark.gpu
+def test_streaming_beta_calibration_equals_the_two_step_path(tmp_path):
+    """stream_beta_calibration=True (not a reference kwarg): beta from one sweep that never materialises the
+    {t: noisy bank} dictionary must equal set_noisy_proj_ref + empirical_beta (same generator, same draw order)."""
+    bank = orc.synthetic_bank(70, 4, 16, 16).numpy()
+    common = dict(scale=0.33, sigma=3.15, quantile=0.25, scheduler=_TinyScheduler(), device="cuda")
+    two_step = _build("threshold", "kernel_fast", bank, tmp_path, proj_noisy_ref_path_for_beta=str(tmp_path / "noisy.pt"),
+                      **common)
+    assert os.path.exists(str(tmp_path / "noisy.pt"))
+    common["scheduler"] = _TinyScheduler()
+    streamed = _build("threshold", "kernel_fast", bank, tmp_path, stream_beta_calibration=True,
+                      proj_noisy_ref_path_for_beta=str(tmp_path / "never_written.pt"), **common)
+    assert not os.path.exists(str(tmp_path / "never_written.pt"))
+    assert two_step.beta_threshold > 0
+    assert abs(streamed.beta_threshold / two_step.beta_threshold - 1.0) <= 1e-5
