@@ -578,12 +578,14 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------ weights
-// Thread = (bank row, query row): sum the K-split partials in split order, k = exp(-dist / 2 sigma^2), write the
-// weight planes P [Npad][128] bf16 (stacked query index contiguous: hi parts in columns [0,64), lo parts in [64,128)),
-// which phase B reads as an MN-major B operand.  A block of 256 threads walks `rows_per_block` bank rows four at a
-// time (<= 128 blocks: every SM ingests its share of the partials at ~45 GB/s); everything is coalesced.  The block
-// that finishes last sums the per-block z partials in block order (z, kmax, the flat-regime mark): round 1 did that in
-// a second launch (k_umma_zreduce, ~4 us), and summed ||x||^2 parts in a loop of dependent L2 loads (8 of 12.7 us).
+// Thread = (bank row, query row): sum the K-split partials in split order, k = exp(-dist / 2 sigma^2) (or the SPELL
+// weight, weight_from_dot), write the weight planes P [Npad][128] bf16 (stacked query index contiguous: hi parts in
+// columns [0,64), lo parts in [64,128)), which phase B reads as an MN-major B operand.  Everything is coalesced and
+// every load of a row is issued before the first use.  A block has 4 or 16 row lanes (256 / 1024 threads) and walks
+// `rows_per_block` bank rows; per block one z partial (sums | maxima), summed in block order by
+//   - phase B's idle epilogue warps (dense accumulate, AccumEpi::zpart: 1024-thread blocks of 16-32 rows, few partials),
+//   - k_umma_zreduce (block-sparse mode, which needs kmax before phase B; z-only passes of empirical_beta), or
+//   - the last block of this kernel (`arrivals` != null; measured slower with few fat blocks, not used).
 constexpr int kWRows = 4;          // bank rows a block handles per step (and per k_umma_siglist block)
 
 // The dot of query row q is S_T[..][col0 + q] (+ S_T[..][col0 + lo_off + q] when lo_off > 0: stacked operand).

@@ -82,10 +82,16 @@ def main():
         torch.cuda.synchronize()
         e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        sync_word = torch.zeros(1, device=dev)
+        for _ in range(4):                  # untimed queued work: the host gets ahead of the GPU before step 0
+            flush.zero_()
+            flush_rd.sum()
         for i in range(args.steps):
             x.copy_(x_src)
             flush.zero_()
             flush_rd.sum()
+            if world > 1:
+                dist.all_reduce(sync_word)  # the flush takes a different time on every GPU: line the ranks up (as bench.py does)
             e0[i].record()
             step()
             e1[i].record()
