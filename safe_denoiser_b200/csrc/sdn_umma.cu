@@ -187,22 +187,8 @@ k_umma_qprep(const float* __restrict__ xq, int Q, int64_t D, __nv_bfloat16* __re
 // kUChunk K-blocks and the epilogue warps drain the finished one into fp32 registers (round-to-nearest adds).
 constexpr int kUChunk = 4;
 
-constexpr int kUThreadsA = 320;   // TMA warp, MMA warp, 4 epilogue warps, 4 query-operand warps (InlineX)
+constexpr int kUThreadsA = 192;   // TMA warp, MMA warp, 4 epilogue warps
 constexpr uint32_t kAccColsA = 128;
-
-// Query operand made inside phase A (round 2): instead of a query-prepare launch that writes bf16 hi/lo planes of the
-// query for TMA to fetch (8 us at cfg3, on every batched call and on every shard), four warps of every phase-A CTA read
-// their K block of the fp32 query rows from global memory (L2 hits: the rows are shared by all row tiles), split them
-// into bf16 hi / lo and write the MMA operand tile in the 128-byte-swizzled K-major layout TMA would have produced; they
-// are the X producers of the stage ring (full[s] counts their four arrivals + the TMA thread's).  The CTAs of row tile 0
-// also deliver ||x_q||^2 over their K range (one part per K split, summed by the weights step).
-struct InlineX {
-  const float* xq;      // [Q][D] fp32 query rows of the pass; null: X planes come from tm_x (query-prepare kernels)
-  int Q; int64_t D;
-  float* xsq_part;      // [G][ksplit][64] or null (the caller supplies ||x||^2)
-  float* zero_word;     // scalar CTA (0,0) clears (the logging mean of the fused epilogue), or null
-  StartClear clr;       // lists / counters CTA (0,0) resets
-};
 
 // Weights step fused into phase A (round 2): the CTA that delivers the LAST K-split partial of a row tile turns the
 // tile's dots into weights -- sums the K-split partials in split order, k = exp(-dist / 2 sigma^2), writes the weight
@@ -229,7 +215,7 @@ __device__ __forceinline__ void dots_tail(const DotsTail& T, const float* __rest
                                           int row0, float (*zs)[kUQ], float (*zm)[kUQ], int* s_flag, uint8_t* stage,
                                           uint64_t* bar, float* sq_s) {
   const int t = threadIdx.x, q = t & (kUQ - 1), rsub = t >> 6;       // 192 threads: 3 row subsets x 64 query rows
-  const int kSub = (int)blockDim.x >> 6;           // 3 row subsets (192 threads) or 5 (320: with the InlineX warps)
+  constexpr int kSub = kUThreadsA / kUQ;
   // The K-split partials of the tile come into the (now idle) pipeline stages by bulk copies -- a round of R rows is
   // ksplit contiguous pieces of R x 512 bytes: register loads from L2 were latency-bound (54 us for this step at cfg3).
   const int R = min(kUBankTile, (int)(kPipeBytes / ((uint32_t)ksplit * kUStack * 4)));
@@ -355,16 +341,13 @@ __device__ __forceinline__ void dots_tail(const DotsTail& T, const float* __rest
 template <int G>
 __global__ void __launch_bounds__(kUThreadsA, 1)
 k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
-            const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_xraw,
-            float* __restrict__ S_T, int64_t split_stride,
-            int kblocks_total, int ksplit, int use_lo, const DotsTail tail, const InlineX ix) {
+            const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int64_t split_stride,
+            int kblocks_total, int ksplit, int use_lo, const DotsTail tail) {
   using C = UCfg<G>;
-  const bool inline_x = ix.xq != nullptr;
   extern __shared__ unsigned char smem_raw[];
   __shared__ float zs[kUThreadsA / kUQ][kUQ], zm[kUThreadsA / kUQ][kUQ];
   __shared__ int s_flag;
   __shared__ uint64_t tail_bar;
-  __shared__ uint64_t rawfull[kUMaxStages];          // InlineX: the fp32 query rows of a stage have landed
   __shared__ float sq_s[kUBankTile];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -385,17 +368,11 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
     const int kc = (kb0 + i) * kUK;
     if (what & 2) {
-      if (inline_x) {
-        // fp32 rows [64 G queries][64 d] (rows past Q: zero fill) land in the X slot; the operand warps convert in place
-        u_mbar_expect_tx(&rawfull[s], (uint32_t)G * kTileBytes);
-        u_tma_2d(st, &tm_xraw, kc, 0, &rawfull[s]);
-      } else {
 #pragma unroll
-        for (int g = 0; g < G; ++g) u_tma_2d(st + (size_t)g * kTileBytes, &tm_x, kc, g * kUStack, &sm.full[s]);
-      }
+      for (int g = 0; g < G; ++g) u_tma_2d(st + (size_t)g * kTileBytes, &tm_x, kc, g * kUStack, &sm.full[s]);
     }
     if (!(what & 1)) return;
-    u_mbar_expect_tx(&sm.full[s], (uint32_t)((inline_x ? 0 : G) + 1 + (use_lo ? 1 : 0)) * kTileBytes);
+    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     if (tail.keep_from_row >= 0) {
       u_tma_2d_hint(st + C::kHiOff, &tm_hi, kc, row0, &sm.full[s], bank_policy);
       if (use_lo) u_tma_2d_hint(st + C::kLoOff, &tm_lo, kc, row0, &sm.full[s], bank_policy);
@@ -407,89 +384,26 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int npre = min(nkb, C::kStages);
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], inline_x ? 5 : 1); u_mbar_init(&sm.empty[s], 1); }
+    for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4); }
     u_mbar_init(&tail_bar, 1);
-    for (int s = 0; s < kUMaxStages; ++s) u_mbar_init(&rawfull[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the first stages need nothing but this thread's own barriers: their HBM latency overlaps the TMEM
     // allocation and the start-up barrier (the kernel is fill/drain bound at N ~ 3000); the bank tiles do not even
     // need the query-prepare kernel to have finished, only the X tiles do
-    u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo); u_prefetch_map(&tm_xraw);
+    u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
     for (int i = 0; i < npre; ++i) load_stage(i, 1);
     pdl_wait();
     for (int i = 0; i < npre; ++i) load_stage(i, 2);
   }
   pdl_wait();
-  if (inline_x && blockIdx.x == 0 && blockIdx.y == 0) {
-    // first CTA of the pass: what the query-prepare kernel used to reset (nothing of this pass uses it before phase A ends)
-    start_clear(ix.clr);
-    if (ix.zero_word && threadIdx.x == 0) *ix.zero_word = 0.f;
-  }
   if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * kAccColsA);
   u_fence_before();
   __syncthreads();
   u_fence_after();
   const uint32_t tmem = *sm.tmem_base;
 
-  if (warp >= 6) {
-    // ---- query-operand producers (InlineX): thread = (query row, run of 8-element chunks) of every K block
-    if (inline_x) {
-      // The fp32 rows of the K block arrive by TMA in the X slot of the stage (a fetch with LDG, even two K blocks ahead,
-      // made phase A 43 -> 64-72 us: an L2 round trip under the bank stream is longer than two stages last).  16 lanes
-      // cover the 256 bytes of a row: a warp instruction reads two whole rows, conflict-free.  All 128 threads read
-      // their pieces into registers, meet at a named barrier, and only then overwrite the slot with the operand tiles.
-      const int w = warp - 6;                                // 0..3: 16 G query rows each
-      const int r2 = lane >> 4, piece = lane & 15;           // row within the pair, 16-byte piece (4 floats) of the row
-      constexpr int NI = 8 * G;                              // pieces per thread and K block
-      const uint32_t lo_tile = G == 1 ? 0u : kTileBytes;
-      auto row_of = [&](int j) { return w * (16 * G) + j * 2 + r2; };
-      float ss[NI];
-#pragma unroll
-      for (int j = 0; j < NI; ++j) ss[j] = 0.f;
-#pragma unroll 1
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % C::kStages;
-        uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
-        u_mbar_wait(&rawfull[s], (uint32_t)((i / C::kStages) & 1));
-        float4 v[NI];
-#pragma unroll
-        for (int j = 0; j < NI; ++j) v[j] = *reinterpret_cast<const float4*>(st + (uint32_t)row_of(j) * 256u + (uint32_t)piece * 16u);
-        asm volatile("bar.sync 3, 128;" ::: "memory");       // every piece is in registers before the slot is rewritten
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const uint32_t q = (uint32_t)row_of(j);
-          // hi part of query q: tile 0, row q; lo part: G = 1 -> tile 0, row 64 + q; G = 2 -> tile 1, row q
-          const uint32_t hi_row = q, lo_row = G == 1 ? (uint32_t)kUQ + q : q;
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(v[j].x), h1 = __float2bfloat16_rn(v[j].y);
-          const __nv_bfloat16 h2 = __float2bfloat16_rn(v[j].z), h3 = __float2bfloat16_rn(v[j].w);
-          const __nv_bfloat162 hp0 = __halves2bfloat162(h0, h1), hp1 = __halves2bfloat162(h2, h3);
-          const __nv_bfloat162 lp0 = __floats2bfloat162_rn(v[j].x - __bfloat162float(h0), v[j].y - __bfloat162float(h1));
-          const __nv_bfloat162 lp1 = __floats2bfloat162_rn(v[j].z - __bfloat162float(h2), v[j].w - __bfloat162float(h3));
-          ss[j] = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, ss[j]))));
-          // 128-byte swizzle as TMA writes it: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
-          const uint32_t c = (uint32_t)piece >> 1, half8 = ((uint32_t)piece & 1u) * 8u;
-          *reinterpret_cast<uint2*>(st + hi_row * 128u + ((c ^ (hi_row & 7u)) << 4) + half8) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&hp0), *reinterpret_cast<const uint32_t*>(&hp1));
-          *reinterpret_cast<uint2*>(st + lo_tile + lo_row * 128u + ((c ^ (lo_row & 7u)) << 4) + half8) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&lp0), *reinterpret_cast<const uint32_t*>(&lp1));
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> the tensor core's proxy
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.full[s])) : "memory");
-      }
-      // ||x_q||^2 over this CTA's K range: one part per K split, from the CTAs of row tile 0 (16 lanes per row)
-#pragma unroll
-      for (int j = 0; j < NI; ++j) {
-        float t = ss[j];
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        const int q = row_of(j);
-        if (ix.xsq_part && blockIdx.x == 0 && piece == 0)
-          ix.xsq_part[((int64_t)(q / kUQ) * ksplit + blockIdx.y) * kUQ + (q % kUQ)] = q < ix.Q ? t : 0.f;
-      }
-    }
-  } else if (warp == 0) {
+  if (warp == 0) {
     if (lane == 0) {
       for (int i = npre; i < nkb; ++i) {
         u_mbar_wait(&sm.empty[i % C::kStages], (uint32_t)(((i / C::kStages) + 1) & 1));
@@ -1263,18 +1177,6 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
   return r == CUDA_SUCCESS ? SDN_OK : SDN_E_PARAM;
 }
 
-// 2-D fp32 row-major tensor [rows][cols], box [box_rows][box_cols], no swizzle (rows of the box contiguous in smem).
-int make_map_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 4};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? SDN_OK : SDN_E_PARAM;
-}
-
 }  // namespace
 
 int tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
@@ -1324,7 +1226,7 @@ UmmaLayout umma_layout(int64_t Q, int64_t N, int64_t D) {
   // row-block flags | kmax[G 64] | count[G 64] | dense (4 words) | rows[G 64][cap] | ks[G 64][cap]
   L.off_f = o; o += (size_t)L.nflags * 4 + G * kUQ * 4 + G * kUQ * 4 + 16 + G * kUQ * kListCap * 8 + 256;
   o = (o + 255) / 256 * 256;
-  L.off_q = o; o += G * (size_t)std::max(L.xsq_nparts, 64) * kUQ * 4;   // ||x||^2 parts (query prepare: D / 1024; in phase A: one per K split)
+  L.off_q = o; o += G * L.xsq_nparts * kUQ * 4;              // ||x||^2 partials of the fused query prepare
   o = (o + 255) / 256 * 256;
   L.off_c = o; o += (size_t)(L.npad / kUBankTile + 2) * 4;   // arrival counters of the weights step (fused: one per row tile + 1)
   o = (o + 255) / 256 * 256;
@@ -1526,49 +1428,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   // k_umma_weights + k_umma_zreduce launches.  Measured slower (cfg3: dots 41 -> 64 us against 12.7 + 4 us saved): one
   // SM ingests the tile's K-split partials at ~45 GB/s.  Kept for tiny shards / experiments, off by default.
   static const bool fuse_weights = [] { const char* e = getenv("SDN_UMMA_FUSED_WEIGHTS"); return e && atoi(e) != 0; }();
-  // SDN_UMMA_INLINE_X=1: the query operand is made inside phase A (InlineX) instead of by a query-prepare launch.
-  // Measured (profiles/r02_experiments.txt): no gain -- under graph replay + PDL the query-prepare launch already hides
-  // behind phase A's prologue, and the in-place conversion costs phase A 2.5 us (one query group) to 130 us (two groups,
-  // N = 30 000); cfg3 92.2 us either way, N = 375 shard 38.9 -> 41.0 us.  Off by default.
-  static const bool want_inline = [] { const char* e = getenv("SDN_UMMA_INLINE_X"); return e && atoi(e) != 0; }();
-  const bool inline_x = !fuse_weights && want_inline;
-  const int xsq_nparts = inline_x ? L.ksplit : L.xsq_nparts;
-  int pid = -1;
-  InlineX ix{};
-  CUtensorMap tm_xraw = tm_x;        // placeholder when the query-prepare kernels make the planes
-  if (inline_x) {
-    ix.xq = xq; ix.Q = (int)Q; ix.D = D; ix.xsq_part = xsq ? nullptr : xsq_part; ix.zero_word = zero_word;
-    if (sparse) { ix.clr.lists = lists; ix.clr.lists.ncount = G * kUQ; ix.clr.nflags = nflags; }
-    ix.clr.counters = counters; ix.clr.ncounters = row_tiles + 2;
-    // the query rows change from call to call (but not under CUDA-graph replay): a few recent maps are kept
-    struct XMap { int dev; const void* xq; int64_t Q, D; int G; CUtensorMap m; uint64_t stamp; };
-    static XMap xcache[8];
-    static int xcache_n = 0;
-    static uint64_t xclock = 0;
-    static std::mutex xmu;
-    std::lock_guard<std::mutex> lk(xmu);
-    XMap* hit = nullptr;
-    for (int i = 0; i < xcache_n && !hit; ++i)
-      if (xcache[i].dev == dev && xcache[i].xq == xq && xcache[i].Q == Q && xcache[i].D == D && xcache[i].G == G) hit = &xcache[i];
-    if (!hit) {
-      XMap c{};
-      const int rc = make_map_f32(&c.m, xq, (uint64_t)Q, (uint64_t)D, (uint32_t)(G * kUQ), kUK);
-      if (rc) return rc;
-      c.dev = dev; c.xq = xq; c.Q = Q; c.D = D; c.G = G;
-      int slot = xcache_n;
-      if (xcache_n == 8) {
-        slot = 0;
-        for (int i = 1; i < 8; ++i) if (xcache[i].stamp < xcache[slot].stamp) slot = i;
-      } else {
-        ++xcache_n;
-      }
-      xcache[slot] = c;
-      hit = &xcache[slot];
-    }
-    hit->stamp = ++xclock;
-    tm_xraw = hit->m;
-  } else {
-  pid = g_prof.begin(xsq ? "k_umma_xprep" : "k_umma_qprep", st);
+  int pid = g_prof.begin(xsq ? "k_umma_xprep" : "k_umma_qprep", st);
   for (int g = 0; g < G; ++g) {
     StartClear clr{};
     if (g == 0) {
@@ -1587,8 +1447,6 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     SDN_LAUNCHED();
   }
   g_prof.end(pid, st);
-
-  }
 
   // phase A: split K (= D) so that roughly every SM gets one task; the last arrival of a row tile makes its weights
   const int kblocks = (int)(D / kUK);
@@ -1612,11 +1470,11 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   pid = g_prof.begin("k_umma_dots", st);
   const bool pdl = pdl_enabled();
   if (G == 1)
-    launch_ex(k_umma_dots<1>, dim3(row_tiles, L.ksplit), dim3(inline_x ? kUThreadsA : kUThreadsA - 128), kUSmemBytes, st, pdl,
-              tm_x, tm_hiA, tm_loA, tm_xraw, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail, ix);
+    launch_ex(k_umma_dots<1>, dim3(row_tiles, L.ksplit), dim3(kUThreadsA), kUSmemBytes, st, pdl,
+              tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
   else
-    launch_ex(k_umma_dots<2>, dim3(row_tiles, L.ksplit), dim3(inline_x ? kUThreadsA : kUThreadsA - 128), kUSmemBytes, st, pdl,
-              tm_x, tm_hiA, tm_loA, tm_xraw, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail, ix);
+    launch_ex(k_umma_dots<2>, dim3(row_tiles, L.ksplit), dim3(kUThreadsA), kUSmemBytes, st, pdl,
+              tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
 
@@ -1634,7 +1492,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     const int rpb = fuse_z ? fuse_z_rpb : kWRows;
     launch_ex(k_umma_weights, dim3((unsigned)cdiv(L.npad, rpb)), dim3((fuse_z ? kWMaxLanes : kWRows) * kUQ), 0, st, pdl,
               (const float*)S_T, L.split_stride, L.ksplit, g * kUQ, G == 1 ? kUQ : 0, sqnorm, xsq ? xsq + g * kUQ : nullptr,
-              (const float*)(xsq_part + (int64_t)g * xsq_nparts * kUQ), xsq_nparts, (int)N, group_rows(g), inv2s2, power,
+              (const float*)(xsq_part + (int64_t)g * L.xsq_nparts * kUQ), L.xsq_nparts, (int)N, group_rows(g), inv2s2, power,
               alpha, P + (int64_t)g * L.npad * kUStack, zpart + (int64_t)g * L.zpart_stride,
               k_out ? k_out + (int64_t)g * kUQ * N : nullptr, rpb, (int)L.npad, (int*)nullptr, z + g * kUQ, kmax + g * kUQ,
               sparse ? lists.dense : (int*)nullptr);
