@@ -20,6 +20,8 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "sdn_internal.h"
@@ -204,6 +206,7 @@ struct DotsTail {
   float inv2s2, alpha; int power;
   __nv_bfloat16* P; int64_t p_group_stride;      // [G][Npad][128]
   int interleave_k;         // K splits take every ksplit-th K block instead of a contiguous range
+  int merged;               // tm_bank is the 3-D map [D][N][2 planes]: hi + lo tile in one TMA request
   int keep_from_row;        // bank rows >= this are loaded with L2 evict_last, the others evict_first (-1: no hints):
                             // phase B starts with the rows phase A read last and finds them in the L2
   float* zpart; int64_t zpart_stride;            // [G][row tiles][sums 64 | maxima 64]
@@ -342,7 +345,8 @@ __device__ __forceinline__ void dots_tail(const DotsTail& T, const float* __rest
 template <int G>
 __global__ void __launch_bounds__(kUThreadsA, 1)
 k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
-            const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ S_T, int64_t split_stride,
+            const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_bank,
+            float* __restrict__ S_T, int64_t split_stride,
             int kblocks_total, int ksplit, int use_lo, const DotsTail tail) {
   using C = UCfg<G>;
   extern __shared__ unsigned char smem_raw[];
@@ -378,7 +382,9 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     if (!(what & 1)) return;
     u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
-    if (tail.keep_from_row >= 0) {
+    if (tail.merged && use_lo && tail.keep_from_row < 0) {
+      u_tma_3d(st + C::kHiOff, &tm_bank, kc, row0, 0, &sm.full[s]);      // hi tile | lo tile: one 32 KiB request
+    } else if (tail.keep_from_row >= 0) {
       u_tma_2d_hint(st + C::kHiOff, &tm_hi, kc, row0, &sm.full[s], bank_policy);
       if (use_lo) u_tma_2d_hint(st + C::kLoOff, &tm_lo, kc, row0, &sm.full[s], bank_policy);
     } else {
@@ -396,7 +402,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     // the first stages need nothing but this thread's own barriers: their HBM latency overlaps the TMEM
     // allocation and the start-up barrier (the kernel is fill/drain bound at N ~ 3000); the bank tiles do not even
     // need the query-prepare kernel to have finished, only the X tiles do
-    u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
+    u_prefetch_map(&tm_x); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo); u_prefetch_map(&tm_bank);
     for (int i = 0; i < npre; ++i) load_stage(i, 1);
     pdl_wait();
     for (int i = 0; i < npre; ++i) load_stage(i, 2);
@@ -789,6 +795,7 @@ struct AccumEpi {
   // by this kernel's epilogue warps while the main loop runs -- instead of a k_umma_zreduce launch (6 us at cfg3).  The
   // CTAs of d-block 0 also write the sums to `z` (which then is an output).  Null: read z.
   const float* zpart; int nzpart; int64_t zpart_stride; float* z_out;
+  int merged;           // tm_bank4 / tm_p3 are the merged-request maps
   int z_only;           // zpart given but no correction here (N-sharded banks: the merge kernel applies it): write z_out only
 };
 
@@ -797,7 +804,8 @@ struct AccumEpi {
 template <bool CHUNKED, int G>
 __global__ void __launch_bounds__(UCfg<G>::kThreads, 1)
 k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
-             const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q,
+             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_bank4,
+             const __grid_constant__ CUtensorMap tm_p3, float* __restrict__ num, int64_t D, int Q,
              int rblocks_total, int nsplit, int64_t split_stride, int use_lo, int p_group_rows, const int* rowflags,
              const int* __restrict__ list_count, const int* __restrict__ dense_flag, const AccumEpi epi) {
   using C = UCfg<G>;
@@ -833,13 +841,21 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     if (what & 2) {
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        u_tma_2d(st + (size_t)g * kTileBytes, &tm_p, 0, g * p_group_rows + rc, &sm.full[s]);
-        u_tma_2d(st + (size_t)g * kTileBytes + 8192, &tm_p, 64, g * p_group_rows + rc, &sm.full[s]);
+        if (epi.merged) {             // both halves of the weight tile: one 16 KiB request
+          u_tma_3d(st + (size_t)g * kTileBytes, &tm_p3, 0, g * p_group_rows + rc, 0, &sm.full[s]);
+        } else {
+          u_tma_2d(st + (size_t)g * kTileBytes, &tm_p, 0, g * p_group_rows + rc, &sm.full[s]);
+          u_tma_2d(st + (size_t)g * kTileBytes + 8192, &tm_p, 64, g * p_group_rows + rc, &sm.full[s]);
+        }
       }
     }
     if (!(what & 1)) return;
     u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
-    // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart
+    // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart -- one 4-D request of 32 KiB for all four
+    if (epi.merged && use_lo) {
+      u_tma_4d(st + C::kHiOff, &tm_bank4, 0, rc, d0 / 64, 0, &sm.full[s]);
+      return;
+    }
     u_tma_2d(st + C::kHiOff, &tm_hi, d0, rc, &sm.full[s]);
     u_tma_2d(st + C::kHiOff + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
     if (use_lo) {
@@ -854,7 +870,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4 * G); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
+    u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo); u_prefetch_map(&tm_bank4); u_prefetch_map(&tm_p3);
     // the bank tiles of the first stages do not depend on the weights: they stream while the weights kernels finish
     for (int it = 0; it < npre; ++it) load_stage(it, epi.reverse ? nrb - 1 - it % nrb : it % nrb, it / nrb, 1);
     pdl_wait();
@@ -1182,6 +1198,19 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
   return r == CUDA_SUCCESS ? SDN_OK : SDN_E_PARAM;
 }
 
+// bf16 tensor of `rank` dimensions (innermost first; strides in BYTES for dimensions 1..rank-1, need not be sorted),
+// 128-byte swizzle on the innermost dimension.
+int make_map_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* stride_bytes,
+                const uint32_t* box) {
+  cuuint64_t d[5]; cuuint64_t st[4]; cuuint32_t b[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = stride_bytes[i];
+  const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SDN_OK : SDN_E_PARAM;
+}
+
 }  // namespace
 
 int tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
@@ -1330,7 +1359,7 @@ int configure_kernels() {
 }
 
 struct AccumLaunch {
-  CUtensorMap tm_p, tm_hi, tm_lo;
+  CUtensorMap tm_p, tm_hi, tm_lo, tm_bank4, tm_p3;
   float* num; int64_t D; int64_t split_stride; int Q, rblocks, nsplit, use_lo, p_group_rows;
   const int* flags; const int* count; const int* dense;
   AccumEpi e;
@@ -1340,10 +1369,12 @@ template <int G>
 void launch_accum(const AccumLaunch& a, cudaStream_t st) {
   const dim3 grid(a.gridx, a.nsplit);
   if (a.chunked)
-    launch_ex(k_umma_accum<true, G>, grid, dim3(UCfg<G>::kThreads), kUSmemBytes, st, a.pdl, a.tm_p, a.tm_hi, a.tm_lo, a.num,
+    launch_ex(k_umma_accum<true, G>, grid, dim3(UCfg<G>::kThreads), kUSmemBytes, st, a.pdl, a.tm_p, a.tm_hi, a.tm_lo,
+              a.tm_bank4, a.tm_p3, a.num,
               a.D, a.Q, a.rblocks, a.nsplit, a.split_stride, a.use_lo, a.p_group_rows, a.flags, a.count, a.dense, a.e);
   else
-    launch_ex(k_umma_accum<false, G>, grid, dim3(UCfg<G>::kThreads), kUSmemBytes, st, a.pdl, a.tm_p, a.tm_hi, a.tm_lo, a.num,
+    launch_ex(k_umma_accum<false, G>, grid, dim3(UCfg<G>::kThreads), kUSmemBytes, st, a.pdl, a.tm_p, a.tm_hi, a.tm_lo,
+              a.tm_bank4, a.tm_p3, a.num,
               a.D, a.Q, a.rblocks, a.nsplit, a.split_stride, a.use_lo, a.p_group_rows, a.flags, a.count, a.dense, a.e);
 }
 }  // namespace
@@ -1373,12 +1404,13 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
 
   // tensor maps depend only on (device, planes, workspace, N, D, G): a small per-process cache (several projectors /
   // devices in one process each keep their entry; least recently used is replaced)
-  struct MapCache { int dev; const void* planes; const void* ws; int64_t N, D; int G; CUtensorMap m[6]; uint64_t stamp; };
+  struct MapCache { int dev; const void* planes; const void* ws; int64_t N, D; int G; CUtensorMap m[9]; bool merged; uint64_t stamp; };
   static MapCache cache[8];
   static int cache_n = 0;
   static uint64_t cache_clock = 0;
   static std::mutex cache_mu;
-  CUtensorMap tm_x, tm_hiA, tm_loA, tm_p, tm_hiB, tm_loB;
+  CUtensorMap tm_x, tm_hiA, tm_loA, tm_p, tm_hiB, tm_loB, tm_bankA, tm_bankB, tm_p3;
+  bool merged = false;
   {
     std::lock_guard<std::mutex> lk(cache_mu);
     MapCache* hit = nullptr;
@@ -1394,6 +1426,25 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
       if ((rc = make_map(&c.m[3], P, (uint64_t)G * L.npad, kUStack, kUK, 64))) return rc;
       if ((rc = make_map(&c.m[4], hi, N, D, kUK, 64))) return rc;
       if ((rc = make_map(&c.m[5], lo, N, D, kUK, 64))) return rc;
+      // merged requests: hi + lo tile of phase A in one 3-D box; both planes x both 64-wide halves of phase B's bank^T
+      // tile in one 4-D box; both halves of a weight tile in one 3-D box.  (Older drivers may refuse the unsorted strides:
+      // the 2-D maps above then do the job.)
+      // Measured: accepted by the driver, bit-identical results, NO change in time (cfg3 phase A 41.5, phase B 49.7 us
+      // either way) -- the request count is not what bounds these kernels.  Off unless SDN_UMMA_MERGED_TMA=1.
+      static const bool want_merged = [] { const char* e = getenv("SDN_UMMA_MERGED_TMA"); return e && atoi(e) != 0; }();
+      c.merged = want_merged;
+      if (c.merged) {
+        const uint64_t dA[3] = {(uint64_t)D, (uint64_t)N, 2}, sA[2] = {(uint64_t)D * 2, (uint64_t)N * D * 2};
+        const uint32_t bA[3] = {kUK, kUBankTile, 2};
+        const uint64_t dB[4] = {64, (uint64_t)N, (uint64_t)(D / 64), 2}, sB[3] = {(uint64_t)D * 2, 128, (uint64_t)N * D * 2};
+        const uint32_t bB[4] = {64, kUK, 2, 2};
+        const uint64_t dP[3] = {64, (uint64_t)G * L.npad, 2}, sP[2] = {(uint64_t)kUStack * 2, 128};
+        const uint32_t bP[3] = {64, kUK, 2};
+        const int r6 = make_map_nd(&c.m[6], hi, 3, dA, sA, bA), r7 = make_map_nd(&c.m[7], hi, 4, dB, sB, bB),
+                  r8 = make_map_nd(&c.m[8], P, 3, dP, sP, bP);
+        if (getenv("SDN_UMMA_DEBUG")) fprintf(stderr, "[sdn_umma] merged tensor maps: phase A %d, phase B bank %d, weights %d\n", r6, r7, r8);
+        if (r6 || r7 || r8) c.merged = false;
+      }
       c.dev = dev; c.planes = planes; c.ws = ws; c.N = N; c.D = D; c.G = G;
       int slot = cache_n;
       if (cache_n == 8) {
@@ -1407,6 +1458,8 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     }
     hit->stamp = ++cache_clock;
     tm_x = hit->m[0]; tm_hiA = hit->m[1]; tm_loA = hit->m[2]; tm_p = hit->m[3]; tm_hiB = hit->m[4]; tm_loB = hit->m[5];
+    merged = hit->merged;
+    tm_bankA = merged ? hit->m[6] : tm_hiA; tm_bankB = merged ? hit->m[7] : tm_hiB; tm_p3 = merged ? hit->m[8] : tm_p;
   }
 
   // significant-row lists, shared by the groups of the pass (flags and the dense mark are unions over the groups;
@@ -1470,6 +1523,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   // on by default: cfg3 phase A 43.6 -> 41.5 us, step 92.2 -> 90.1 us (SDN_UMMA_INTERLEAVE_K=0 restores contiguous ranges)
   static const int interleave_k = [] { const char* e = getenv("SDN_UMMA_INTERLEAVE_K"); return e ? atoi(e) : 1; }();
   tail.interleave_k = interleave_k;
+  tail.merged = merged ? 1 : 0;
   const bool l2keep = keep_mb > 0 && (num || epi) && L.nsplit == 1;
   if (l2keep) {
     const int64_t keep_rows = std::min<int64_t>(L.npad, (int64_t)keep_mb * 1000000 / (D * 4));
@@ -1479,10 +1533,10 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   const bool pdl = pdl_enabled();
   if (G == 1)
     launch_ex(k_umma_dots<1>, dim3(row_tiles, L.ksplit), dim3(kUThreadsA), kUSmemBytes, st, pdl,
-              tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
+              tm_x, tm_hiA, tm_loA, tm_bankA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
   else
     launch_ex(k_umma_dots<2>, dim3(row_tiles, L.ksplit), dim3(kUThreadsA), kUSmemBytes, st, pdl,
-              tm_x, tm_hiA, tm_loA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
+              tm_x, tm_hiA, tm_loA, tm_bankA, S_T, L.split_stride, kblocks, L.ksplit, bf16_bank ? 0 : 1, tail);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
 
@@ -1534,6 +1588,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     e = *epi;
   }
   e.reverse = l2keep ? 1 : 0;
+  e.merged = merged ? 1 : 0;
   if (fuse_z) {
     e.zpart = zpart; e.nzpart = (int)cdiv(L.npad, fuse_z_rpb); e.zpart_stride = L.zpart_stride; e.z_out = z;
     e.z_only = epi ? 0 : 1;
@@ -1549,7 +1604,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   }
   pid = g_prof.begin("k_umma_accum", st);
   AccumLaunch al{};
-  al.tm_p = tm_p; al.tm_hi = tm_hiB; al.tm_lo = tm_loB; al.num = nsplit > 1 ? part : num; al.D = D; al.Q = (int)Q; al.rblocks = rblocks;
+  al.tm_p = tm_p; al.tm_hi = tm_hiB; al.tm_lo = tm_loB; al.tm_bank4 = tm_bankB; al.tm_p3 = tm_p3; al.num = nsplit > 1 ? part : num; al.D = D; al.Q = (int)Q; al.rblocks = rblocks;
   al.nsplit = nsplit; al.split_stride = nsplit > 1 ? Q * D : 0; al.use_lo = bf16_bank ? 0 : 1; al.p_group_rows = (int)L.npad;
   al.flags = sparse ? lists.flags : nullptr; al.count = sparse ? lists.count : nullptr;
   al.dense = sparse ? lists.dense : nullptr; al.e = e;

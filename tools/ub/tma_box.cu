@@ -79,6 +79,20 @@ int main() {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kStages * kTile);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const char* names[] = {"linear 16 KiB", "box [128 rows][64 bf16]", "2 x box [64 rows][64 bf16]"};
+  // second part: the same patterns over a span that stays in the L2 (1024 rows = 32 MiB), few CTAs: what ONE SM's TMA
+  // unit delivers per pattern when neither HBM nor the L2 is the limit
+  for (int mode = 0; mode < 3; ++mode)
+    for (int g : {148, 37, 8, 1}) {
+      const int tiles = 4096;
+      k<<<g, 128, kStages * kTile>>>(m128, m64, buf, mode, 1024, tiles, sink);
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0);
+      k<<<g, 128, kStages * kTile>>>(m128, m64, buf, mode, 1024, tiles, sink);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      const double bytes = (double)g * tiles * kTile;
+      printf("L2-resident  %-28s %3d CTAs: %8.1f GB/s  (%5.1f GB/s per SM)\n", names[mode], g, bytes / ms / 1e6, bytes / ms / 1e6 / g);
+    }
   for (int mode = 0; mode < 3; ++mode)
     for (int g : {148, 128}) {
       const int tiles = 4096;                                  // 64 MiB per CTA
