@@ -286,6 +286,23 @@ int sdn_conditioning_host(const float* bank, const float* sqnorm, const void* pl
                           float* denom_host, int32_t path, void* stream);
 void sdn_host_release(void);
 
+/* ---- host-buffer calls in flight: the serving / throughput form of the e2e path -----------
+ * The reference runs one conditioning() per sampler step and prompt (models/textuals_visual/
+ * modified_safree_diffusion_pipeline_threshold_time.py:550-576); prompts are independent, so a server keeps several
+ * calls in flight.  A pipe owns `slots` (1..8) device staging areas with one stream each for a fixed (Q, N, D).
+ * submit: enqueue H2D of x0_in_host [Q,D] -> fused conditioning over the device-resident prepared bank -> D2H of the
+ * corrected query into x0_out_host [Q,D] (may alias x0_in_host) and of denom_host [Q]; returns without waiting.
+ * wait: block until that slot's results are in the host buffers.  The bank must be complete before the first submit
+ * (there is no caller stream to order against).  Host buffers should be pinned (pageable memory makes the copies
+ * synchronous).  SDN_E_UNSUPPORTED from submit: the shape has no fused sequence, use sdn_conditioning_host.
+ */
+int sdn_host_pipe_create(int64_t Q, int64_t N, int64_t D, int32_t slots, void** pipe_out);
+int sdn_host_pipe_submit(void* pipe, int32_t slot, const float* bank, const float* sqnorm, const void* planes,
+                         const float* x0_in_host, float* x0_out_host, float* denom_host,
+                         float inv_two_sigma_sq, int32_t dist_power, float bank_alpha, float eps, float scale);
+int sdn_host_pipe_wait(void* pipe, int32_t slot);
+void sdn_host_pipe_destroy(void* pipe);
+
 #ifdef __cplusplus
 }
 #endif

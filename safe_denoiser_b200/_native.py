@@ -50,6 +50,10 @@ SIGNATURES = {
     "sdn_conditioning_host": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _i32, _f, _i32, _f, _f, _f,
                                         _p, _i32, _p]),
     "sdn_host_release": (None, []),
+    "sdn_host_pipe_create": (C.c_int, [_i64, _i64, _i64, _i32, _p]),
+    "sdn_host_pipe_submit": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, _f, _i32, _f, _f, _f]),
+    "sdn_host_pipe_wait": (C.c_int, [_p, _i32]),
+    "sdn_host_pipe_destroy": (None, [_p]),
 }
 
 

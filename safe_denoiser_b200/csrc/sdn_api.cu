@@ -441,4 +441,84 @@ int sdn_conditioning_host(const float* bank, const float* sqnorm, const void* pl
   return SDN_OK;
 }
 
+// ------------------------------------------------------------------ host-buffer calls in flight (throughput)
+// A serving loop has independent requests: while one's corrected query travels back over PCIe the next one's query can
+// travel in and a third can be on the SMs.  A pipe owns `slots` staging areas, each with its own stream; submit enqueues
+// H2D copy -> fused conditioning -> D2H copies on the slot's stream and returns, wait blocks until that slot's results
+// are in the host buffers.  Work on one slot is stream-ordered, so re-submitting a slot without waiting is safe for the
+// device buffers (the caller's host output is overwritten, of course).
+namespace {
+struct HostPipe {
+  int device = 0;
+  int64_t Q = 0, N = 0, D = 0;
+  int nslots = 0;
+  size_t qd = 0, qv = 0, ws = 0, slot_bytes = 0;
+  char* dev = nullptr;
+  cudaStream_t streams[8] = {};
+};
+}  // namespace
+
+int sdn_host_pipe_create(int64_t Q, int64_t N, int64_t D, int32_t slots, void** pipe_out) {
+  if (!pipe_out) return SDN_E_NULL;
+  if (Q <= 0 || N <= 0 || D <= 0 || slots < 1 || slots > 8) return SDN_E_SHAPE;
+  HostPipe* hp = new HostPipe();
+  SDN_CUDA_OK(cudaGetDevice(&hp->device));
+  hp->Q = Q; hp->N = N; hp->D = D; hp->nslots = slots;
+  hp->qd = align_up(sizeof(float) * Q * D, 256);
+  hp->qv = align_up(sizeof(float) * Q, 256);
+  hp->ws = align_up(sdn_repel_workspace_bytes(Q, N, D, SDN_PATH_AUTO), 256);
+  hp->slot_bytes = hp->qd + 2 * hp->qv + hp->ws;      // x0 | z | denom | workspace
+  cudaError_t e = cudaMalloc(&hp->dev, hp->slot_bytes * slots);
+  for (int i = 0; e == cudaSuccess && i < slots; ++i) e = cudaStreamCreateWithFlags(&hp->streams[i], cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    sdn_host_pipe_destroy(hp);
+    return (int)e;
+  }
+  *pipe_out = hp;
+  return SDN_OK;
+}
+
+int sdn_host_pipe_submit(void* pipe, int32_t slot, const float* bank, const float* sqnorm, const void* planes,
+                         const float* x0_in_host, float* x0_out_host, float* denom_host, float inv_two_sigma_sq,
+                         int32_t dist_power, float bank_alpha, float eps, float scale) {
+  HostPipe* hp = static_cast<HostPipe*>(pipe);
+  if (!hp || !x0_in_host || !x0_out_host || !denom_host) return SDN_E_NULL;
+  if (slot < 0 || slot >= hp->nslots) return SDN_E_PARAM;
+  int cur_dev = 0;
+  SDN_CUDA_OK(cudaGetDevice(&cur_dev));
+  if (cur_dev != hp->device) return SDN_E_DEVICE;
+  char* p = hp->dev + (size_t)slot * hp->slot_bytes;
+  float* x0 = reinterpret_cast<float*>(p);
+  float* z = reinterpret_cast<float*>(p + hp->qd);
+  float* denom = reinterpret_cast<float*>(p + hp->qd + hp->qv);
+  void* wsp = p + hp->qd + 2 * hp->qv;
+  cudaStream_t st = hp->streams[slot];
+  const int64_t Q = hp->Q, D = hp->D;
+  SDN_CUDA_OK(cudaMemcpyAsync(x0, x0_in_host, sizeof(float) * Q * D, cudaMemcpyHostToDevice, st));
+  const int rc = sdn_conditioning_fused(bank, sqnorm, planes, hp->N, D, x0, Q, inv_two_sigma_sq, dist_power, bank_alpha, eps,
+                                        scale, 0.f, 0, nullptr, z, nullptr, denom, nullptr, nullptr, nullptr, wsp, hp->ws,
+                                        SDN_PATH_AUTO, st);
+  if (rc) return rc;          // SDN_E_UNSUPPORTED: a shape without a fused sequence (use sdn_conditioning_host)
+  SDN_CUDA_OK(cudaMemcpyAsync(x0_out_host, x0, sizeof(float) * Q * D, cudaMemcpyDeviceToHost, st));
+  SDN_CUDA_OK(cudaMemcpyAsync(denom_host, denom, sizeof(float) * Q, cudaMemcpyDeviceToHost, st));
+  return SDN_OK;
+}
+
+int sdn_host_pipe_wait(void* pipe, int32_t slot) {
+  HostPipe* hp = static_cast<HostPipe*>(pipe);
+  if (!hp) return SDN_E_NULL;
+  if (slot < 0 || slot >= hp->nslots) return SDN_E_PARAM;
+  SDN_CUDA_OK(cudaStreamSynchronize(hp->streams[slot]));
+  return SDN_OK;
+}
+
+void sdn_host_pipe_destroy(void* pipe) {
+  HostPipe* hp = static_cast<HostPipe*>(pipe);
+  if (!hp) return;
+  for (int i = 0; i < 8; ++i)
+    if (hp->streams[i]) { cudaStreamSynchronize(hp->streams[i]); cudaStreamDestroy(hp->streams[i]); }
+  if (hp->dev) cudaFree(hp->dev);
+  delete hp;
+}
+
 }  // extern "C"

@@ -207,6 +207,7 @@ struct DotsTail {
   __nv_bfloat16* P; int64_t p_group_stride;      // [G][Npad][128]
   int interleave_k;         // K splits take every ksplit-th K block instead of a contiguous range
   int merged;               // tm_bank is the 3-D map [D][N][2 planes]: hi + lo tile in one TMA request
+  int dbg_noshared;         // experiment (WRONG results): the X tiles are loaded for the first stages only
   int keep_from_row;        // bank rows >= this are loaded with L2 evict_last, the others evict_first (-1: no hints):
                             // phase B starts with the rows phase A read last and finds them in the L2
   float* zpart; int64_t zpart_stride;            // [G][row tiles][sums 64 | maxima 64]
@@ -376,12 +377,13 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const int s = i % C::kStages;
     uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
     const int kc = (kb0 + i * kstride) * kUK;
-    if (what & 2) {
+    const bool skip_x = tail.dbg_noshared && i >= C::kStages;
+    if ((what & 2) && !skip_x) {
 #pragma unroll
       for (int g = 0; g < G; ++g) u_tma_2d(st + (size_t)g * kTileBytes, &tm_x, kc, g * kUStack, &sm.full[s]);
     }
     if (!(what & 1)) return;
-    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
+    u_mbar_expect_tx(&sm.full[s], (uint32_t)((skip_x ? 0 : G) + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     if (tail.merged && use_lo && tail.keep_from_row < 0) {
       u_tma_3d(st + C::kHiOff, &tm_bank, kc, row0, 0, &sm.full[s]);      // hi tile | lo tile: one 32 KiB request
     } else if (tail.keep_from_row >= 0) {
@@ -796,6 +798,7 @@ struct AccumEpi {
   // CTAs of d-block 0 also write the sums to `z` (which then is an output).  Null: read z.
   const float* zpart; int nzpart; int64_t zpart_stride; float* z_out;
   int merged;           // tm_bank4 / tm_p3 are the merged-request maps
+  int dbg_noshared;     // experiment (WRONG results): the weight tiles are loaded for the first stages only
   int z_only;           // zpart given but no correction here (N-sharded banks: the merge kernel applies it): write z_out only
 };
 
@@ -838,7 +841,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
     const int rc = (rb0 + i) * kUK;                   // first bank row of this block
     // P tiles: per group two boxes of [64 rows][64 stacked q] (hi parts, lo parts), 8 KiB apart
-    if (what & 2) {
+    const bool skip_p = epi.dbg_noshared && it >= C::kStages;
+    if ((what & 2) && !skip_p) {
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (epi.merged) {             // both halves of the weight tile: one 16 KiB request
@@ -850,7 +854,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       }
     }
     if (!(what & 1)) return;
-    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
+    u_mbar_expect_tx(&sm.full[s], (uint32_t)((skip_p ? 0 : G) + 1 + (use_lo ? 1 : 0)) * kTileBytes);
     // bank^T tiles: two boxes of [64 rows][64 d] per plane, 8 KiB apart -- one 4-D request of 32 KiB for all four
     if (epi.merged && use_lo) {
       u_tma_4d(st + C::kHiOff, &tm_bank4, 0, rc, d0 / 64, 0, &sm.full[s]);
@@ -1149,6 +1153,277 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   }
 }
 
+// ------------------------------------------------------------------------------------------ phase B on every SM
+// k_umma_accum runs D / 128 CTAs (128 of the 148 SMs at SD-1.4 shapes) and every CTA is paced at one 48 KiB stage per
+// ~0.85 us whatever is switched off (stages, requests, MMAs: profiles/r02_experiments.txt), so idle SMs are lost
+// bandwidth.  Here the (d-block, 64-row block) units are dealt in d-block-major order in equal contiguous ranges to
+// min(#SMs, units) CTAs (one per SM: all co-resident).  A d-block whose row blocks span several CTAs (2-3 at SD-1.4 shapes)
+// is finished by the CTA that holds its FIRST row block -- for that CTA it is the last segment of its range -- and the
+// others (for which it is the first or the only segment) publish their partial in `scratch` and count themselves in on a
+// flag per (d-block, query group).  The finisher therefore waits, at the very end of its work, for partials that were
+// mostly written long before; it adds them in slot order (deterministic).  A first version chained the partials in CTA
+// order (each CTA waiting for its predecessor's LAST segment): that serialises the whole grid, 514 us instead of 49.
+// Dense accumulate, chains of <= 64 row blocks (N <= 4096: no chunked TMEM drain needed), no bank-row split.
+struct BalArgs {
+  float* scratch;       // [dblocks][slots][G * 64 query rows][128 d] partials of the non-finishing CTAs
+  unsigned* flags;      // [dblocks * G] arrivals (zeroed by the query-prepare kernel of the pass)
+  int rblocks;          // 64-row blocks of the bank
+  int slots;            // most CTAs a d-block can span, minus the finisher
+};
+
+template <int G>
+__global__ void __launch_bounds__(UCfg<G>::kThreads, 1)
+k_umma_accum_bal(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_hi,
+                 const __grid_constant__ CUtensorMap tm_lo, float* __restrict__ num, int64_t D, int Q, int use_lo,
+                 int p_group_rows, const BalArgs bal, const AccumEpi epi) {
+  using C = UCfg<G>;
+  pdl_launch_dependents();
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ float z_half[G][2][kUQ], z_sum[G][kUQ];
+  const USmem sm = u_carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rblocks = bal.rblocks;
+  const int dblocks = (int)(D / kUDBlock);
+  const int units = dblocks * rblocks;
+  const int ncta = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int per = units / ncta, rem = units % ncta;
+  const int u0 = cta * per + min(cta, rem), u1 = u0 + per + (cta < rem ? 1 : 0);
+  const int nun = u1 - u0;
+  auto cta_of_unit = [&](int u) { return u < (per + 1) * rem ? u / (per + 1) : rem + (u - (per + 1) * rem) / max(per, 1); };
+
+  auto load_stage = [&](int it, int what) {
+    const int u = u0 + it, db = u / rblocks, rb = u - db * rblocks;
+    const int d0 = db * kUDBlock, rc = rb * kUK;
+    const int s = it % C::kStages;
+    uint8_t* st = sm.tiles + (size_t)s * C::kStageBytes;
+    if (what & 2) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        u_tma_2d(st + (size_t)g * kTileBytes, &tm_p, 0, g * p_group_rows + rc, &sm.full[s]);
+        u_tma_2d(st + (size_t)g * kTileBytes + 8192, &tm_p, 64, g * p_group_rows + rc, &sm.full[s]);
+      }
+    }
+    if (!(what & 1)) return;
+    u_mbar_expect_tx(&sm.full[s], (uint32_t)(G + 1 + (use_lo ? 1 : 0)) * kTileBytes);
+    u_tma_2d(st + C::kHiOff, &tm_hi, d0, rc, &sm.full[s]);
+    u_tma_2d(st + C::kHiOff + 8192, &tm_hi, d0 + 64, rc, &sm.full[s]);
+    if (use_lo) {
+      u_tma_2d(st + C::kLoOff, &tm_lo, d0, rc, &sm.full[s]);
+      u_tma_2d(st + C::kLoOff + 8192, &tm_lo, d0 + 64, rc, &sm.full[s]);
+    }
+  };
+  const int npre = min(nun, C::kStages);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) { u_mbar_init(&sm.full[s], 1); u_mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { u_mbar_init(&sm.acc_full[b], 1); u_mbar_init(&sm.acc_empty[b], 4 * G); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    u_prefetch_map(&tm_p); u_prefetch_map(&tm_hi); u_prefetch_map(&tm_lo);
+    // the bank tiles of the first stages do not depend on the weights: they stream while the weights kernel finishes
+    for (int it = 0; it < npre; ++it) load_stage(it, 1);
+    pdl_wait();
+    for (int it = 0; it < npre; ++it) load_stage(it, 2);
+  }
+  pdl_wait();
+  if (warp == 1) u_tmem_alloc(sm.tmem_base, 2 * C::kAccCols);
+  u_fence_before();
+  __syncthreads();
+  u_fence_after();
+  const uint32_t tmem = *sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = npre; it < nun; ++it) {
+        u_mbar_wait(&sm.empty[it % C::kStages], (uint32_t)(((it / C::kStages) + 1) & 1));
+        load_stage(it, 3);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_full = u_idesc(kUDBlock, kUStack, 1, 1);   // hi * [P_hi | P_lo]
+      constexpr uint32_t id_half = u_idesc(kUDBlock, kUQ, 1, 1);       // lo * P_hi
+      int seg = 0;
+      for (int it = 0; it < nun;) {
+        const int db = (u0 + it) / rblocks;
+        const int it_end = min(nun, (db + 1) * rblocks - u0);          // the units of this d-block that are mine
+        const int buf = seg & 1;
+        if (seg >= 2) {
+          u_mbar_wait(&sm.acc_empty[buf], (uint32_t)(((seg >> 1) + 1) & 1));
+          u_fence_after();
+        }
+        const uint32_t acc = tmem + (uint32_t)buf * C::kAccCols;
+        for (int first = it; it < it_end; ++it) {
+          const int s = it % C::kStages;
+          u_mbar_wait(&sm.full[s], (uint32_t)((it / C::kStages) & 1));
+          u_fence_after();
+          const uint32_t base = u_smem(sm.tiles + (size_t)s * C::kStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < kUK / 16; ++kk) {
+            const uint64_t ah = u_desc(base + C::kHiOff + kk * 2048, 8192, 1024);        // bank^T, MN-major
+            const uint64_t al = u_desc(base + C::kLoOff + kk * 2048, 8192, 1024);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const uint64_t b = u_desc(base + (uint32_t)g * kTileBytes + kk * 2048, 8192, 1024);   // P_g^T, MN-major
+              u_mma(acc + (uint32_t)g * kUStack, ah, b, id_full, (it > first || kk > 0) ? 1u : 0u);
+              if (use_lo) u_mma(acc + (uint32_t)g * kUStack, al, b, id_half, 1u);
+            }
+          }
+          u_commit(&sm.empty[s]);
+        }
+        u_commit(&sm.acc_full[buf]);
+        ++seg;
+      }
+    }
+  } else {
+    // epilogue: warps 2..5 serve query group 0, warps 6..9 group 1; TMEM lane = d within the block, column = stacked q
+    const int lq = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int tg = (warp - 2 - 4 * g) * 32 + lane;               // 0..127 within the group's four warps
+    const int Qg = min(kUQ, Q - g * kUQ);
+    const int64_t qoff = (int64_t)g * kUQ * D;
+    float* const numg = num ? num + qoff : nullptr;
+    const float* zg = epi.z ? epi.z + g * kUQ : nullptr;
+    if (epi.zpart) {
+      const int qz = tg & (kUQ - 1), half = tg >> 6;
+      const float* zp = epi.zpart + (int64_t)g * epi.zpart_stride + qz;
+      float a = 0.f;
+      for (int b0 = half; b0 < epi.nzpart; b0 += 16) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = b0 + 2 * u < epi.nzpart ? __ldcg(zp + (int64_t)(b0 + 2 * u) * kUStack) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a += v[u];
+      }
+      z_half[g][half][qz] = a;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      if (tg < kUQ) {
+        const float zz = z_half[g][0][tg] + z_half[g][1][tg];
+        z_sum[g][tg] = zz;
+        if (cta == 0 && epi.z_out && tg < Qg) epi.z_out[g * kUQ + tg] = zz;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      zg = epi.z_only ? nullptr : z_sum[g];
+    }
+    float* const x0g = epi.x0 ? epi.x0 + qoff : nullptr;
+    float* const negg = epi.neg_out ? epi.neg_out + qoff : nullptr;
+    float* const denomg = epi.denom_out ? epi.denom_out + g * kUQ : nullptr;
+    int32_t* const gateg = epi.gate_out ? epi.gate_out + g * kUQ : nullptr;
+    const uint32_t tcol = (uint32_t)(g * kUStack);
+    float msum = 0.f;
+    int seg = 0;
+#pragma unroll 1
+    for (int it = 0; it < nun; ++seg) {
+      const int db = (u0 + it) / rblocks;
+      const int rb_first = (u0 + it) - db * rblocks;
+      const int it_end = min(nun, (db + 1) * rblocks - u0);
+      const int rb_last = (u0 + it_end - 1) - db * rblocks;
+      it = it_end;
+      // the CTA that holds the d-block's first row block finishes it (that segment is the LAST of its range, or the whole
+      // d-block); every other CTA of the chain only publishes its partial (its FIRST or only segment)
+      const bool finisher = rb_first == 0;
+      const int c_first = finisher ? cta : cta_of_unit(db * rblocks);
+      const int ncontrib = finisher ? cta_of_unit(db * rblocks + rblocks - 1) - cta : 0;
+      (void)rb_last;
+      const int buf = seg & 1;
+      u_mbar_wait(&sm.acc_full[buf], (uint32_t)((seg >> 1) & 1));
+      u_fence_after();
+      const int dl = lq * 32 + lane;
+      const int64_t d = (int64_t)db * kUDBlock + dl;
+      const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)buf * C::kAccCols + tcol;
+      // [d-block][slot][group][q][128 d]; slot = position in the chain - 1
+      const int64_t slot_stride = (int64_t)G * kUQ * kUDBlock;
+      float* const sc0 = bal.scratch + ((int64_t)db * bal.slots * G + g) * kUQ * kUDBlock + dl;
+      float* const sc = sc0 + (int64_t)(finisher ? 0 : cta - c_first - 1) * slot_stride;
+      unsigned* const fl = bal.flags + db * G + g;
+      if (ncontrib > 0) {
+        if (lane == 0) {
+          uint32_t spin = 0;
+          while (u_ld_acquire(fl) < (unsigned)ncontrib) {
+            __nanosleep(64);
+            if (++spin > (1u << 24)) __trap();     // a broken chain must not hang the GPU
+          }
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int c = 0; c < kUQ / 32; ++c) {
+        float a[32];
+        {
+          float b[32];
+          u_tmem_ld32(tl + (uint32_t)(c * 32), a);            // hi*P_hi + lo*P_hi, queries [32c, 32c+32)
+          u_tmem_ld32(tl + (uint32_t)(kUQ + c * 32), b);      // hi*P_lo
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] += b[j];
+        }
+        if (!finisher) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(sc + (int64_t)(c * 32 + j) * kUDBlock, a[j]);
+          continue;
+        }
+#pragma unroll 1
+        for (int s = 0; s < ncontrib; ++s) {                   // mine + slot 0 + slot 1 ...: a fixed order
+          float pv[32];
+          const float* ps = sc0 + (int64_t)s * slot_stride;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] = __ldcg(ps + (int64_t)(c * 32 + j) * kUDBlock);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] += pv[j];
+        }
+        if (zg) {
+          float xv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int q = min(c * 32 + j, Qg - 1);
+            xv[j] = x0g ? __ldcg(x0g + (int64_t)q * D + d) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int q = c * 32 + j;
+            if (q < Qg) {
+              const float dn = zg[q] + epi.eps;
+              const int64_t o = (int64_t)q * D + d;
+              const float n = a[j] / dn;
+              if (numg) numg[o] = a[j];
+              if (negg) negg[o] = n;
+              if (x0g) x0g[o] = fmaf(-epi.scale, n, xv[j]);
+              msum += fminf(fmaxf(n, -1e10f), 1e10f);
+              if (db == 0 && lq == 0 && lane == 0) {
+                if (denomg) denomg[q] = dn;
+                if (gateg) gateg[q] = (!(epi.flags & SDN_EPI_GATE) || dn > epi.gate_thr) ? 1 : 0;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int q = c * 32 + j;
+            if (q < Qg) numg[(int64_t)q * D + d] = a[j];
+          }
+        }
+      }
+      u_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(u_smem(&sm.acc_empty[buf])) : "memory");
+      if (!finisher) {
+        // publish: every thread's stores, then a gpu-scope fence, then the group's barrier, then ONE arrival
+        __threadfence();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (tg == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(fl) : "memory");
+      }
+    }
+    if (zg && epi.mean_out) {
+      msum = warp_sum(msum);
+      if (lane == 0) atomicAdd(epi.mean_out, msum * epi.inv_qd);
+    }
+  }
+  u_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    u_fence_after();
+    u_tmem_dealloc(tmem, 2 * C::kAccCols);
+  }
+}
+
 // num[q][d] = sum_s part[s][q][d] in split order (deterministic; the splits used to atomicAdd into num).  Exits like
 // k_umma_accum does when the listed accumulate already produced the result.
 __global__ void __launch_bounds__(256)
@@ -1235,6 +1510,8 @@ struct UmmaLayout {
   int xsq_nparts;
   size_t off_x, off_s, off_p, off_z, off_f, off_q, off_c, off_n, total;
   int nsplit;          // bank-row splits of phase B (partials in the workspace, summed in order)
+  bool bal;            // shape the balanced phase B (k_umma_accum_bal) takes: no row split, <= 64 row blocks
+  int bal_slots;       // partial slots per d-block of the balanced phase B
   // per-group strides (elements)
   int64_t split_stride, zpart_stride;
 };
@@ -1262,13 +1539,22 @@ UmmaLayout umma_layout(int64_t Q, int64_t N, int64_t D) {
   o = (o + 255) / 256 * 256;
   L.off_q = o; o += G * L.xsq_nparts * kUQ * 4;              // ||x||^2 partials of the fused query prepare
   o = (o + 255) / 256 * 256;
-  L.off_c = o; o += (size_t)(L.npad / kUBankTile + 2) * 4;   // arrival counters of the weights step (fused: one per row tile + 1)
+  // arrival counters of the weights step (fused: one per row tile + 1), then the chain flags of the balanced phase B
+  L.off_c = o; o += (size_t)(L.npad / kUBankTile + 2 + (D / kUDBlock) * G) * 4;
   o = (o + 255) / 256 * 256;
   {
     const int dblocks = (int)(D / kUDBlock), rblocks = (int)(L.npad / kUK);
     L.nsplit = std::max(1, std::min(rblocks / 8, kNumSMs / std::max(1, dblocks)));
   }
-  L.off_n = o; o += L.nsplit > 1 ? (size_t)L.nsplit * (size_t)Q * D * 4 : 0;   // phase-B split partials [nsplit][Q][D]
+  // phase-B split partials [nsplit][Q][D], or the hand-over buffer of the balanced phase B [D/128][64 G][128]
+  L.bal = L.nsplit == 1 && L.npad / kUK <= kBChunk;
+  {
+    const int dblocks = (int)(D / kUDBlock), rblocks = (int)(L.npad / kUK);
+    const int per = std::max(1, dblocks * rblocks / std::min(kNumSMs, dblocks * rblocks));
+    L.bal_slots = std::max(1, (rblocks - 1 + per - 1) / per);
+  }
+  L.off_n = o;
+  o += L.nsplit > 1 ? (size_t)L.nsplit * (size_t)Q * D * 4 : (L.bal ? (size_t)L.bal_slots * G * kUQ * (size_t)D * 4 : 0);
   L.total = (o + 255) / 256 * 256;
   return L;
 }
@@ -1355,6 +1641,7 @@ int configure_kernels() {
   SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_dots<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
   SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<false, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
   SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum<true, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
+  SDN_CUDA_OK(cudaFuncSetAttribute(k_umma_accum_bal<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUSmemBytes));
   return SDN_OK;
 }
 
@@ -1491,7 +1778,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     StartClear clr{};
     if (g == 0) {
       if (sparse) { clr.lists = lists; clr.lists.ncount = G * kUQ; clr.nflags = nflags; }
-      clr.counters = counters; clr.ncounters = row_tiles + 2;
+      clr.counters = counters; clr.ncounters = row_tiles + 2 + (int)(D / kUDBlock) * G;
     }
     const float* xg = xq + (int64_t)g * kUQ * D;
     __nv_bfloat16* pg = xpl + (int64_t)g * kUQ * D;      // hi part of the group's row 0; lo parts G * 64 rows below
@@ -1524,6 +1811,8 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   static const int interleave_k = [] { const char* e = getenv("SDN_UMMA_INTERLEAVE_K"); return e ? atoi(e) : 1; }();
   tail.interleave_k = interleave_k;
   tail.merged = merged ? 1 : 0;
+  static const int dbg_noshared = [] { const char* e = getenv("SDN_UMMA_DBG_NOSHARED"); return e ? atoi(e) : 0; }();
+  tail.dbg_noshared = dbg_noshared & 1;
   const bool l2keep = keep_mb > 0 && (num || epi) && L.nsplit == 1;
   if (l2keep) {
     const int64_t keep_rows = std::min<int64_t>(L.npad, (int64_t)keep_mb * 1000000 / (D * 4));
@@ -1589,6 +1878,7 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   }
   e.reverse = l2keep ? 1 : 0;
   e.merged = merged ? 1 : 0;
+  e.dbg_noshared = (dbg_noshared >> 1) & 1;
   if (fuse_z) {
     e.zpart = zpart; e.nzpart = (int)cdiv(L.npad, fuse_z_rpb); e.zpart_stride = L.zpart_stride; e.z_out = z;
     e.z_only = epi ? 0 : 1;
@@ -1612,7 +1902,21 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   al.pdl = pdl;
   // chains longer than kBChunk row blocks are split over the two TMEM accumulators (fp32 register drain)
   al.chunked = (rblocks + nsplit - 1) / nsplit > kBChunk;
-  if (G == 1) launch_accum<1>(al, st); else launch_accum<2>(al, st);
+  // phase B on every SM (SDN_UMMA_BALANCED=1; measured no gain: cfg3 51.6 us against 49.5 us -- the kernel is bounded by a
+  // chip-wide rate, not by the 20 idle SMs) when the shape allows and nothing is skipped
+  static const bool want_bal = [] { const char* e = getenv("SDN_UMMA_BALANCED"); return e && atoi(e) != 0; }();
+  if (want_bal && L.bal && !sparse && dblocks * rblocks > dblocks) {
+    BalArgs bal{};
+    bal.scratch = part; bal.flags = reinterpret_cast<unsigned*>(counters + row_tiles + 2); bal.rblocks = rblocks;
+    bal.slots = L.bal_slots;
+    const int nb = std::min(kNumSMs, dblocks * rblocks);
+    if (G == 1)
+      launch_ex(k_umma_accum_bal<1>, dim3(nb), dim3(UCfg<1>::kThreads), kUSmemBytes, st, pdl, tm_p, tm_hiB, tm_loB, num, D, (int)Q,
+                bf16_bank ? 0 : 1, (int)L.npad, bal, e);
+    else
+      launch_ex(k_umma_accum_bal<2>, dim3(nb), dim3(UCfg<2>::kThreads), kUSmemBytes, st, pdl, tm_p, tm_hiB, tm_loB, num, D, (int)Q,
+                bf16_bank ? 0 : 1, (int)L.npad, bal, e);
+  } else if (G == 1) launch_accum<1>(al, st); else launch_accum<2>(al, st);
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   if (nsplit > 1) {

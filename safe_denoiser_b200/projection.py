@@ -9,6 +9,7 @@ siblings.  The UNet / scheduler objects stay the caller's.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import torch
@@ -484,6 +485,45 @@ def conditioning_host(bank: NegativeBank, x0_host: torch.Tensor, denom_host: tor
         x0_host.data_ptr(), Q, int(normalize_channels), 1.0 / (2.0 * float(sigma) ** 2), 1, 1.0,
         float(eps), float(scale), denom_host.data_ptr(), path, nv.current_stream()))
     return x0_host
+
+
+class HostPipe:
+    """Several host-buffer conditioning() calls in flight (sdn_host_pipe_*): independent requests overlap their
+    PCIe copies with each other's kernels.  `submit(slot, x_in, x_out, denom)` returns at once, `wait(slot)` blocks
+    until x_out / denom hold that slot's result.  Host tensors: contiguous CPU fp32, pinned for real overlap."""
+
+    def __init__(self, bank: NegativeBank, Q: int, slots: int = 3):
+        self.bank, self.Q, self.slots = bank, int(Q), int(slots)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(bank.device):
+            nv.check(nv.lib().sdn_host_pipe_create(self.Q, bank.N, bank.D, self.slots, ctypes.byref(h)))
+        self._h = h
+
+    def submit(self, slot: int, x_in: torch.Tensor, x_out: torch.Tensor, denom: torch.Tensor, sigma: float,
+               scale: float, eps: float = 1e-8):
+        for t in (x_in, x_out, denom):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("host tensors must be contiguous CPU fp32")
+        if x_in.numel() != self.Q * self.bank.D or x_out.numel() != x_in.numel() or denom.numel() != self.Q:
+            raise RuntimeError("host tensors do not match the pipe's (Q, D)")
+        b = self.bank
+        nv.check(nv.lib().sdn_host_pipe_submit(self._h, int(slot), nv.ptr(b.flat), nv.ptr(b.sqnorm), nv.ptr(b.planes),
+                                               x_in.data_ptr(), x_out.data_ptr(), denom.data_ptr(),
+                                               1.0 / (2.0 * float(sigma) ** 2), 1, 1.0, float(eps), float(scale)))
+
+    def wait(self, slot: int):
+        nv.check(nv.lib().sdn_host_pipe_wait(self._h, int(slot)))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            nv.lib().sdn_host_pipe_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def inv_two_sigma_sq(sigma: float) -> float:

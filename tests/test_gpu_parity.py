@@ -335,6 +335,44 @@ def test_host_call_matches_device_call(nv):
     assert rel(dh, dev["denom"]) <= 1e-6
 
 
+@pytest.mark.parametrize("Q,N,planes", [(4, 515, False), (16, 515, True), (64, 700, True)])
+def test_host_pipe_matches_one_call_at_a_time(nv, Q, N, planes):
+    """sdn_host_pipe_*: three host-buffer calls in flight, slots reused without waiting in between; every result is
+    bit-identical to the synchronous sdn_conditioning_host call on the same query."""
+    from safe_denoiser_b200.projection import HostPipe, NegativeBank, conditioning_host
+    bank4 = orc.synthetic_bank(N, 4, 64, 64)
+    bank = NegativeBank(bank4.cuda(), with_planes=planes)
+    torch.cuda.synchronize()
+    queries = [orc.synthetic_queries(bank4, Q, kind).contiguous().pin_memory() for kind in ("near", "far", "near")]
+    want = []
+    for xq in queries:
+        xh, dh = xq.clone().pin_memory(), torch.empty(Q).pin_memory()
+        conditioning_host(bank, xh, dh, 3.15, 0.33)
+        want.append((xh, dh))
+    pipe = HostPipe(bank, Q, slots=3)
+    outs = [torch.empty_like(queries[0]).pin_memory() for _ in range(3)]
+    dens = [torch.empty(Q).pin_memory() for _ in range(3)]
+    for rnd in range(3):                       # rounds 1, 2 re-submit busy slots: stream order keeps them apart
+        for sl in range(3):
+            pipe.submit(sl, queries[sl], outs[sl], dens[sl], 3.15, 0.33)
+    for sl in range(3):
+        pipe.wait(sl)
+    for sl in range(3):
+        assert torch.equal(outs[sl], want[sl][0]), sl
+        assert torch.equal(dens[sl], want[sl][1]), sl
+    # in place (x_out aliases x_in), and argument checks
+    xi = queries[1].clone().pin_memory()
+    pipe.submit(0, xi, xi, dens[0], 3.15, 0.33)
+    pipe.wait(0)
+    assert torch.equal(xi, want[1][0])
+    L = nv.lib()
+    assert L.sdn_host_pipe_wait(pipe._h, 5) == -4
+    assert L.sdn_host_pipe_submit(pipe._h, 0, None, None, None, None, None, None, 1.0, 1, 1.0, 1e-8, 0.3) == -1
+    with pytest.raises(RuntimeError):
+        pipe.submit(0, queries[0][:1], outs[0], dens[0], 3.15, 0.33)
+    pipe.close()
+
+
 def test_errors_are_loud(nv):
     from safe_denoiser_b200.projection import NegativeBank, Projector
     bank = NegativeBank(orc.synthetic_bank(10, 4, 8, 8).cuda())

@@ -1,0 +1,121 @@
+// Micro-benchmark: does the CTA -> address MAPPING of the tcgen05 kernels (not the box shape) set their HBM rate?
+// tma_box.cu walks tiles b, b + grid, ... with k fastest: neighbouring CTAs read neighbouring 128-byte pieces of the same
+// bank rows at the same moment (every DRAM page is consumed whole).  The real kernels do not:
+//   phase B   CTA = one d-block (w = 2 pieces of 128 bytes per row), walks the 64-row blocks: a row's 32 KiB are
+//             read by 128 different CTAs, each at its own pace
+//   phase A   CTA = (128-row tile, K split s), walks K blocks s, s + ksplit, ...
+// Here: loads only, one plane [N = 32768][D = 16384] bf16 (1 GiB), 16 KiB per stage, `st` stages in flight.
+//   mode B(w, h, nsplit): CTA = (column group of w pieces, row split); stage = w boxes [h rows][64 bf16], w * h = 128
+//   mode A(ksplit, interleave): CTA = (row tile, split); stage = one box [128 rows][64 bf16]
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tma_map tma_map.cu -lcuda && ./tma_map
+#include <cstdio>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+constexpr int kMaxStages = 12;
+constexpr uint32_t kTile = 16384;
+constexpr int64_t D = 16384;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void box(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+struct Maps { CUtensorMap m[4]; };   // box rows 128, 64, 32, 16
+
+// mode 0: phase-B mapping (w, h, nsplit); mode 1: phase-A mapping (ksplit = w, interleave = h != 0, row tiles = nsplit)
+__global__ void __launch_bounds__(128, 1) k(const __grid_constant__ Maps maps, int mode, int w, int h, int nsplit, int stages,
+                                             int64_t nrows, unsigned* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[kMaxStages];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  int ntiles;
+  const int b = blockIdx.x;
+  int cg = 0, sp = 0, rt = 0, ks = 0;
+  if (mode == 0) {
+    const int ncg = (int)(D / 64) / w;
+    cg = b % ncg; sp = b / ncg;
+    ntiles = (int)(nrows / h) / nsplit;
+  } else {
+    const int ksplit = w;
+    rt = b / ksplit; ks = b % ksplit;
+    ntiles = (int)(D / 64) / ksplit;
+  }
+  const CUtensorMap* mp = &maps.m[mode == 1 ? 0 : (h == 64 ? 1 : h == 32 ? 2 : 3)];
+  auto issue = [&](int i) {
+    const int s = i % stages;
+    const uint32_t bar = smem_u32(&full[s]), dst = smem_u32(smem + (size_t)s * kTile);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTile) : "memory");
+    if (mode == 0) {
+      const int row = (sp * ntiles + i) * h;
+      for (int j = 0; j < w; ++j) box(dst + j * h * 128, mp, bar, (cg * w + j) * 64, row);
+    } else {
+      const int kb = h ? ks + i * w : ks * ntiles + i;
+      box(dst, mp, bar, kb * 64, rt * 128);
+    }
+  };
+  for (int i = 0; i < stages && i < ntiles; ++i) issue(i);
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i % stages;
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(smem_u32(&full[s])), "r"((uint32_t)((i / stages) & 1)) : "memory");
+    if (i + stages < ntiles) issue(i + stages);
+  }
+  sink[blockIdx.x] = smem[0];
+}
+
+int main() {
+  const int64_t N = 32768;                                     // 1 GiB plane
+  uint8_t* buf; unsigned* sink; uint8_t* flush;
+  cudaMalloc(&buf, (size_t)N * D * 2); cudaMemset(buf, 1, (size_t)N * D * 2);
+  cudaMalloc(&flush, 512u << 20);
+  cudaMalloc(&sink, 4096);
+  void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+  cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  Maps maps;
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)N}; cuuint64_t strides[1] = {(cuuint64_t)D * 2}; cuuint32_t es[2] = {1, 1};
+  const cuuint32_t rows[4] = {128, 64, 32, 16};
+  for (int i = 0; i < 4; ++i) {
+    cuuint32_t bx[2] = {64, rows[i]};
+    enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, dims, strides, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStages * kTile);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto run = [&](const char* name, int mode, int w, int h, int nsplit, int stages, int grid, int64_t nrows) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaMemsetAsync(flush, rep, 512u << 20);
+      cudaEventRecord(e0);
+      k<<<grid, 128, kMaxStages * kTile>>>(maps, mode, w, h, nsplit, stages, nrows, sink);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      if (ms < best) best = ms;
+    }
+    const double bytes = (double)nrows * D * 2;
+    printf("%-58s %3d CTAs x %2d stages, %6.0f MB: %7.1f us  %7.1f GB/s\n", name, grid, stages, bytes / 1e6, best * 1e3, bytes / best / 1e6);
+  };
+  for (int64_t nrows : {(int64_t)32768, (int64_t)6144}) {     // 1 GiB steady state; 201 MB = both planes of cfg3's bank
+    for (int stages : {8, 4}) {
+      run("B: d-block per CTA (w=2 x [64 rows]), all rows", 0, 2, 64, 1, stages, 128, nrows);
+      run("B: w=4 x [32 rows], 2 row splits", 0, 4, 32, 2, stages, 128, nrows);
+      run("B: w=8 x [16 rows], 4 row splits", 0, 8, 16, 4, stages, 128, nrows);
+      const int ks = nrows == 6144 ? 3 : 6;                    // 144 CTAs at 6144 rows; waves of 148 at 32768
+      run("A: (row tile, K split) contiguous K", 1, ks, 0, 0, stages, (int)(nrows / 128) * ks, nrows);
+      run("A: (row tile, K split) interleaved K", 1, ks, 1, 0, stages, (int)(nrows / 128) * ks, nrows);
+    }
+  }
+  printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
