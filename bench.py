@@ -639,6 +639,7 @@ def main():
             "k_umma_weights": npad * 128 * 4 + 128 * npad * 2,
             "k_umma_listed_accum": 0,
             "k_umma_accum": bank_bytes + 128 * npad * 2 + 2 * Q * D * 4,
+            "k_umma_untile": 3 * Q * D * 4,      # tile scratch in, x0 in, x0' out
             "k_flash": step_bytes,
             "k_dots": bank_bytes + Q * D * 4 + Q * n_local * 4, "k_weights": 2 * Q * n_local * 4,
             "k_accum": bank_bytes + Q * n_local * 4 + Q * D * 4,

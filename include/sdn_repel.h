@@ -99,6 +99,8 @@ int32_t sdn_debug_read(uint32_t* words_out, int32_t n);
  * of its pipeline: uint64 [128 CTAs][64 tiles][16 events] (1 MiB) of the last launch, copied to host_out.  Returns
  * the bytes written, 0 when tracing is off or host_out is too small.  (tools/gpu_flash_trace.py prints the stage latencies.) */
 size_t sdn_debug_trace_read(void* host_out, size_t bytes);
+/* Timestamps of the last traced phase-B launch (SDN_UMMA_DBG_NOSHARED bit 10): [256 CTAs][8 events] uint64 ns. */
+size_t sdn_debug_accum_trace_read(void* host_out, size_t bytes);
 
 /* ---- bank -------------------------------------------------------------------------------
  * Derived data of the proj_ref tensor, computed once at load (fast.py:109-111 loads the tensor;

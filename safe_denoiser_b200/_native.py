@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdn_repel.so")
+LIB_PATH = os.environ.get("SDN_REPEL_LIB") or os.path.join(_HERE, "libsdn_repel.so")   # the override is for A/B experiments
 
 PATH_AUTO, PATH_GENERIC, PATH_STREAM, PATH_UMMA, PATH_UMMA_BF16, PATH_FLASH = 0, 1, 2, 3, 4, 5
 EPI_GATE, EPI_RETURN_NEG = 1, 2
@@ -24,6 +24,7 @@ SIGNATURES = {
     "sdn_set_option": (C.c_int, [_i32, _i32]),
     "sdn_debug_read": (_i32, [C.POINTER(C.c_uint32), _i32]),
     "sdn_debug_trace_read": (_sz, [_p, _sz]),
+    "sdn_debug_accum_trace_read": (_sz, [_p, _sz]),
     "sdn_profile_enable": (None, [_i32]),
     "sdn_profile_read": (_i32, [_i32, C.c_char_p, _i32, C.POINTER(C.c_float)]),
     "sdn_bank_prepare": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),

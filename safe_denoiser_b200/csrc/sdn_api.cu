@@ -85,6 +85,7 @@ int32_t sdn_debug_read(uint32_t* words_out, int32_t n) {
 }
 
 size_t sdn_debug_trace_read(void* host_out, size_t bytes) { return flash_trace_read(host_out, bytes); }
+size_t sdn_debug_accum_trace_read(void* host_out, size_t bytes) { return umma_accum_trace_read(host_out, bytes); }
 
 int32_t sdn_repel_path(int64_t Q, int64_t N, int64_t D, int32_t has_planes, int32_t path) {
   if (Q <= 0 || N <= 0 || D <= 0) return SDN_E_SHAPE;

@@ -69,5 +69,6 @@ int flash_run(const void* planes, const float* sqnorm, int64_t N, int64_t D, con
               const FlashEpi* epi, cudaStream_t st);
 int flash_diag_read(uint32_t* out, int n);
 size_t flash_trace_read(void* host_out, size_t bytes);
+size_t umma_accum_trace_read(void* host_out, size_t bytes);   // [256 CTAs][8 events] globaltimer ns of the last traced phase B
 
 }  // namespace sdn

@@ -31,6 +31,15 @@ __device__ __forceinline__ void u_tma_2d(void* dst, const CUtensorMap* map, int 
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(u_smem(dst)), "l"(map), "r"(u_smem(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// plain (1-D) bulk copies of the TMA unit: global -> shared with bytes completed on an mbarrier, shared -> global as
+// part of the thread's bulk async-group (16-byte aligned addresses, size a multiple of 16)
+__device__ __forceinline__ void u_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(u_smem(dst)), "l"(src), "r"(bytes), "r"(u_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void u_bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(u_smem(src)), "r"(bytes) : "memory");
+}
 // same, with an L2 eviction policy made by createpolicy
 __device__ __forceinline__ void u_tma_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
   asm volatile(

@@ -208,6 +208,8 @@ struct DotsTail {
   int interleave_k;         // K splits take every ksplit-th K block instead of a contiguous range
   int merged;               // tm_bank is the 3-D map [D][N][2 planes]: hi + lo tile in one TMA request
   int dbg_noshared;         // experiment (WRONG results): the X tiles are loaded for the first stages only
+  int dbg_nomma;            // experiment (WRONG results): stages are released without any MMA
+  int dbg_nostore;          // experiment (WRONG results): the partial dots are not stored
   int keep_from_row;        // bank rows >= this are loaded with L2 evict_last, the others evict_first (-1: no hints):
                             // phase B starts with the rows phase A read last and finds them in the L2
   float* zpart; int64_t zpart_stride;            // [G][row tiles][sums 64 | maxima 64]
@@ -440,7 +442,7 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           u_fence_after();
           const uint32_t base = u_smem(sm.tiles + (size_t)s * C::kStageBytes);
 #pragma unroll
-          for (int kk = 0; kk < kUK / 16; ++kk) {
+          for (int kk = 0; kk < (tail.dbg_nomma ? (i == c * kUChunk ? 1 : 0) : kUK / 16); ++kk) {
             const uint64_t bh = u_desc(base + C::kHiOff + kk * 32, 16, 1024);
             const uint64_t bl = u_desc(base + C::kLoOff + kk * 32, 16, 1024);
             const uint64_t a0 = u_desc(base + kk * 32, 16, 1024);                 // G = 1: stacked hi|lo; G = 2: hi parts
@@ -481,8 +483,15 @@ k_umma_dots(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     // every K split owns its own partial buffer: plain coalesced stores, summed by k_umma_weights
     const int r = lq * 32 + lane;
     float* dst = S_T + (int64_t)blockIdx.y * split_stride + (int64_t)row0 * kUStack + r;
+    if (tail.dbg_nostore) {                  // experiment (WRONG results): one store instead of 128
+      float v = 0.f;
 #pragma unroll
-    for (int j = 0; j < kUBankTile; ++j) dst[(int64_t)j * kUStack] = sum[j];
+      for (int j = 0; j < kUBankTile; ++j) v += sum[j];
+      dst[0] = v;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kUBankTile; ++j) dst[(int64_t)j * kUStack] = sum[j];
+    }
   }
   u_fence_before();
   __syncthreads();
@@ -788,6 +797,24 @@ constexpr int kMaxActive = 4096;   // row blocks a CTA can index in its active l
 
 // Optional correction fused into phase B's epilogue (one GPU, no bank-row split): x0 -= scale * num / (z + eps).
 // Pointers address query row 0 of the pass; group g of the pass uses rows [64 g, 64 g + 64).
+// experiment: per-CTA timestamps of phase B (AccumEpi::dbg & 64), read by umma_accum_trace_read
+__device__ unsigned long long g_accum_trace[256 * 8];
+__device__ __forceinline__ void accum_trace(int on, int ev) {
+  if (on && blockIdx.y == 0 && blockIdx.x < 256) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_accum_trace[blockIdx.x * 8 + ev] = t;
+  }
+}
+
+__device__ __forceinline__ void accum_trace_dep(int on, int ev, float dep) {
+  if (on && blockIdx.y == 0 && blockIdx.x < 256) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) : "f"(dep) : "memory");
+    g_accum_trace[blockIdx.x * 8 + ev] = t;
+  }
+}
+
 struct AccumEpi {
   const float* z;       // null: no fused correction
   float eps, scale, gate_thr; int flags;
@@ -799,6 +826,11 @@ struct AccumEpi {
   const float* zpart; int nzpart; int64_t zpart_stride; float* z_out;
   int merged;           // tm_bank4 / tm_p3 are the merged-request maps
   int dbg_noshared;     // experiment (WRONG results): the weight tiles are loaded for the first stages only
+  int dbg_nomma;        // experiment (WRONG results): stages are released without any MMA
+  // Non-null: the sums go to a tile-contiguous scratch [D/128][64 G][128] and k_umma_untile applies the fused correction
+  // (and writes the optional outputs) with row-contiguous accesses; null: this kernel updates x0 itself.
+  float* tile_out;
+  int dbg;              // experiment bits (WRONG results): 1 no epilogue loads/stores, 2 no z partial sums, 4 no TMEM loads
   int z_only;           // zpart given but no correction here (N-sharded banks: the merge kernel applies it): write z_out only
 };
 
@@ -813,6 +845,8 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
              const int* __restrict__ list_count, const int* __restrict__ dense_flag, const AccumEpi epi) {
   using C = UCfg<G>;
   pdl_launch_dependents();
+  const int tr = epi.dbg & 64;
+  if (threadIdx.x == 0) accum_trace(tr, 0);
   if (dense_flag || list_count || rowflags) pdl_wait();          // the lists come from the kernels before this one
   if (dense_flag && __ldg(dense_flag)) {
     rowflags = nullptr;                                          // flat regime: no flags were built
@@ -822,7 +856,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint16_t act[kMaxActive];
   __shared__ int nact_s;
-  __shared__ float z_half[G][2][kUQ], z_sum[G][kUQ];
+  __shared__ float z_half[G][2][kUQ], z_sum[G][kUQ], z_rinv[G][kUQ];
   const USmem sm = u_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb0 = (int)((int64_t)blockIdx.y * rblocks_total / nsplit);
@@ -901,6 +935,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
   u_fence_before();
   __syncthreads();
   u_fence_after();
+  if (threadIdx.x == 0) accum_trace(tr, 1);
   const uint32_t tmem = *sm.tmem_base;
   const int nact = nact_s;
   const bool dense = rowflags == nullptr;
@@ -926,7 +961,7 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         u_fence_after();
         const uint32_t base = u_smem(sm.tiles + (size_t)s * C::kStageBytes);
 #pragma unroll
-        for (int kk = 0; kk < kUK / 16; ++kk) {
+        for (int kk = 0; kk < (epi.dbg_nomma ? (first ? 1 : 0) : kUK / 16); ++kk) {
           const uint64_t ah = u_desc(base + C::kHiOff + kk * 2048, 8192, 1024);        // bank^T, MN-major
           const uint64_t al = u_desc(base + C::kLoOff + kk * 2048, 8192, 1024);
 #pragma unroll
@@ -976,7 +1011,11 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     float* const numg = num ? num + qoff + (int64_t)blockIdx.y * split_stride : nullptr;
     // z of this group: from global memory (made by k_umma_zreduce), or summed here from the weights kernel's partials
     const float* zg = epi.z ? epi.z + g * kUQ : nullptr;
-    if (epi.zpart) {
+    if (epi.zpart && (epi.dbg & 2)) {
+      if (threadIdx.x < kUQ + 64) z_sum[g][threadIdx.x & (kUQ - 1)] = 1.f;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      zg = z_sum[g];
+    } else if (epi.zpart) {
       const int t = (warp - 2 - 4 * g) * 32 + lane;          // 0..127 within the group's four warps
       const int qz = t & (kUQ - 1), half = t >> 6;
       const float* zp = epi.zpart + (int64_t)g * epi.zpart_stride + qz;
@@ -1005,64 +1044,98 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     const uint32_t tcol = (uint32_t)(g * kUStack);
     float msum = 0.f;
     if constexpr (!CHUNKED) {
+    // The epilogue runs on ONE warp per scheduler with nothing to overlap it once the bank stream has ended: its
+    // instruction count is kernel time.  A per-element IEEE division, clamps and 64-bit index arithmetic (75 SASS
+    // instructions per element) cost 12 us of the 49.5 us kernel at cfg3 (profiles/r02_experiments.txt); so: 1 / (z + eps)
+    // once per query row, the optional outputs decided once per chunk, denominators and gates written once.
+    if (zg) {
+      const int tq = (warp - 2 - 4 * g) * 32 + lane;
+      if (tq < kUQ) z_rinv[g][tq] = 1.f / (zg[min(tq, Qg - 1)] + epi.eps);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      if (blockIdx.x == 0 && blockIdx.y == 0 && lq == 0) {
+        for (int q = lane; q < Qg; q += 32) {
+          const float dn = zg[q] + epi.eps;
+          if (denomg) denomg[q] = dn;
+          if (gateg) gateg[q] = (!(epi.flags & SDN_EPI_GATE) || dn > epi.gate_thr) ? 1 : 0;
+        }
+      }
+    }
+    const bool extras = numg != nullptr || negg != nullptr || epi.mean_out != nullptr;
     // TMEM lane = d within the block, column = stacked query row
 #pragma unroll 1
     for (int t = 0; t < ntasks; ++t) {
     const int buf = t & 1;
+    const int64_t d = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock + lq * 32 + lane;
     if (nact > 0) {
       u_mbar_wait(&sm.acc_full[buf], (uint32_t)((t >> 1) & 1));
       u_fence_after();
     }
-    const int64_t d = (int64_t)((int)blockIdx.x + t * (int)gridDim.x) * kUDBlock + lq * 32 + lane;
+    if (warp == 2 && lane == 0) accum_trace(tr, 4);
     const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)buf * C::kAccCols + tcol;
+    const unsigned row_bytes = (unsigned)(D * 4);           // D < 2^30 (umma_supported): one IMAD.WIDE per address
 #pragma unroll 1
     for (int c = 0; c < kUQ / 32; ++c) {
-      float a[32], b[32];
-      if (nact > 0) {
+      float a[32];
+      if (nact > 0 && !(epi.dbg & 4)) {
+        float b[32];
         u_tmem_ld32(tl + (uint32_t)(c * 32), a);            // hi*P_hi + lo*P_hi, queries [32c, 32c+32)
         u_tmem_ld32(tl + (uint32_t)(kUQ + c * 32), b);      // hi*P_lo
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] += b[j];
       } else {                                              // no row block of this split matters: the sum is zero
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = b[j] = 0.f;
+        for (int j = 0; j < 32; ++j) a[j] = 0.f;
       }
-      if (zg) {
-        // all loads of the chunk first: the stores below may alias them as far as the compiler knows, and one
-        // load -> store round trip per query row costs ~25 us per launch
-        float xv[32], dn[32];
+      const int qn = Qg - c * 32;                           // query rows of this chunk that exist
+      const int64_t o0 = (int64_t)(c * 32) * D + d;
+      if (tr && c == 0 && warp == 2 && lane == 0) accum_trace_dep(tr, 2, a[31]);      // TMEM loads of chunk 0 done
+      if (epi.dbg & 1) {                                    // experiment (WRONG results): no loads, no stores
+        float v = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int q = min(c * 32 + j, Qg - 1);
-          dn[j] = zg[q] + epi.eps;
-          xv[j] = x0g ? __ldcg(x0g + (int64_t)q * D + d) : 0.f;
+        for (int j = 0; j < 32; ++j) v += a[j];
+        if (v == 1.2345f && x0g) x0g[d] = v;
+      } else if (zg) {
+        const float* ri = z_rinv[g] + c * 32;
+        if (epi.tile_out) {
+          // 128 bytes per warp and query row, rows 512 bytes apart: the pattern of phase A's partial stores.  The same
+          // stores straight into x0 (rows D * 4 bytes apart) take 10 us per CTA (tools/gpu_accum_trace.py).
+          const int dblock = (int)blockIdx.x + t * (int)gridDim.x;
+          float* const tp = epi.tile_out + (((int64_t)dblock * G + g) * kUQ + c * 32) * kUDBlock + lq * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tp[j * kUDBlock] = a[j];
+        } else if (x0g) {
+          // All loads of the chunk first: the stores below may alias them as far as the compiler knows.  (Fetching the
+          // whole column before the wait for the accumulator makes the second chunk's stores take 20 us instead of 10:
+          // tools/gpu_accum_trace.py, profiles/r02_experiments.txt.)
+          char* const pb = reinterpret_cast<char*>(x0g + o0);
+          float xv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            xv[j] = j < qn ? __ldcg(reinterpret_cast<const float*>(pb + (size_t)j * row_bytes)) : 0.f;
+          if (tr && c == 0 && warp == 2 && lane == 0) accum_trace_dep(tr, 3, xv[0] + xv[31]);   // x0 loads of chunk 0 landed
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < qn) *reinterpret_cast<float*>(pb + (size_t)j * row_bytes) = fmaf(-epi.scale, a[j] * ri[j], xv[j]);
+          if (tr && c == 0 && warp == 2 && lane == 0) accum_trace(tr, 7);                        // stores of chunk 0 issued
         }
+        if (extras && !epi.tile_out) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int q = c * 32 + j;
-          if (q < Qg) {
-            const float v = a[j] + b[j];
-            const int64_t o = (int64_t)q * D + d;
-            const float n = v / dn[j];
-            if (numg) numg[o] = v;
-            if (negg) negg[o] = n;
-            if (x0g) x0g[o] = fmaf(-epi.scale, n, xv[j]);
-            msum += fminf(fmaxf(n, -1e10f), 1e10f);
-            if (blockIdx.x == 0 && lq == 0 && lane == 0) {
-              if (denomg) denomg[q] = dn[j];
-              if (gateg) gateg[q] = (!(epi.flags & SDN_EPI_GATE) || dn[j] > epi.gate_thr) ? 1 : 0;
+          for (int j = 0; j < 32; ++j) {
+            if (j < qn) {
+              const float n = a[j] * ri[j];
+              if (numg) numg[o0 + (int64_t)j * D] = a[j];
+              if (negg) negg[o0 + (int64_t)j * D] = n;
+              msum += fminf(fmaxf(n, -1e10f), 1e10f);
             }
           }
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int q = c * 32 + j;
-          if (q < Qg) {
-            float* o = numg + (int64_t)q * D + d;
-            *o = a[j] + b[j];
-          }
-        }
+        for (int j = 0; j < 32; ++j)
+          if (j < qn) numg[o0 + (int64_t)j * D] = a[j];
       }
     }
+    if (warp == 2 && lane == 0) accum_trace(tr, 5);
     u_fence_before();
     __syncwarp();
     if (lane == 0 && nact > 0)
@@ -1140,13 +1213,14 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
       for (int j = 0; j < kUQ; ++j) sum[j] = 0.f;
     }   // units
     }
-    if (zg && epi.mean_out) {
+    if (zg && epi.mean_out && !epi.tile_out) {
       msum = warp_sum(msum);
       if (lane == 0) atomicAdd(epi.mean_out, msum * epi.inv_qd);
     }
   }
   u_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) accum_trace(tr, 6);
   if (warp == 1) {
     u_fence_after();
     u_tmem_dealloc(tmem, 2 * C::kAccCols);
@@ -1424,6 +1498,51 @@ k_umma_accum_bal(const __grid_constant__ CUtensorMap tm_p, const __grid_constant
   }
 }
 
+// x0[q][d] -= scale * num[q][d] / (z[q] + eps) with num read from phase B's tile-contiguous scratch [D/128][64 G][128]:
+// every access of a warp is 512 contiguous bytes.  Same arithmetic as the in-kernel correction
+// (fmaf(-scale, num * (1 / (z + eps)), x0)); the optional outputs (num, neg, mean of the clamped neg) are written here too.
+__global__ void __launch_bounds__(256)
+k_umma_untile(const float* __restrict__ tiles, float* __restrict__ x0, float* __restrict__ num_out,
+              float* __restrict__ neg_out, const float* __restrict__ z, float eps, int Q, int64_t D, int G, float scale,
+              float* __restrict__ mean_out, float inv_qd) {
+  __shared__ float wsum[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t e = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  float m = 0.f;
+  if (e < (int64_t)Q * D) {
+    const int q = (int)(e / D);
+    const int64_t d = e - (int64_t)q * D;
+    const int g = q / kUQ, ql = q % kUQ;
+    const int64_t db = d / kUDBlock;
+    const int dl = (int)(d % kUDBlock);
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(tiles + ((db * G + g) * kUQ + ql) * kUDBlock + dl));
+    float4 x = __ldcg(reinterpret_cast<const float4*>(x0 + e));
+    const float ri = 1.f / (__ldcg(z + q) + eps);
+    const float4 n = make_float4(a.x * ri, a.y * ri, a.z * ri, a.w * ri);
+    x.x = fmaf(-scale, n.x, x.x);
+    x.y = fmaf(-scale, n.y, x.y);
+    x.z = fmaf(-scale, n.z, x.z);
+    x.w = fmaf(-scale, n.w, x.w);
+    *reinterpret_cast<float4*>(x0 + e) = x;
+    if (num_out) *reinterpret_cast<float4*>(num_out + e) = a;
+    if (neg_out) *reinterpret_cast<float4*>(neg_out + e) = n;
+    m = fminf(fmaxf(n.x, -1e10f), 1e10f) + fminf(fmaxf(n.y, -1e10f), 1e10f) + fminf(fmaxf(n.z, -1e10f), 1e10f) +
+        fminf(fmaxf(n.w, -1e10f), 1e10f);
+  }
+  if (mean_out) {                       // the reference's logging scalar: mean of the clamped projection
+    m = warp_sum(m);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += wsum[w];
+      atomicAdd(mean_out, t * inv_qd);
+    }
+  }
+}
+
 // num[q][d] = sum_s part[s][q][d] in split order (deterministic; the splits used to atomicAdd into num).  Exits like
 // k_umma_accum does when the listed accumulate already produced the result.
 __global__ void __launch_bounds__(256)
@@ -1487,6 +1606,12 @@ int make_map_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* di
 }
 
 }  // namespace
+
+size_t umma_accum_trace_read(void* host_out, size_t bytes) {
+  const size_t n = std::min(bytes, sizeof(unsigned long long) * 256 * 8);
+  if (cudaMemcpyFromSymbol(host_out, g_accum_trace, n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 
 int tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
   if (!load_encode()) return SDN_E_DEVICE;
@@ -1562,7 +1687,7 @@ UmmaLayout umma_layout(int64_t Q, int64_t N, int64_t D) {
 
 bool umma_supported(int64_t Q, int64_t N, int64_t D, const void* planes) {
   return planes != nullptr && Q >= 1 && N >= 1 && D >= kUDBlock && D % kUDBlock == 0 &&
-         N < (1ll << 30) && D < (1ll << 31);
+         N < (1ll << 30) && D < (1ll << 30);      // a row of x0 in bytes fits 32 bits (epilogue addressing)
 }
 
 size_t umma_workspace_bytes(int64_t Q, int64_t N, int64_t D) {
@@ -1813,6 +1938,8 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   tail.merged = merged ? 1 : 0;
   static const int dbg_noshared = [] { const char* e = getenv("SDN_UMMA_DBG_NOSHARED"); return e ? atoi(e) : 0; }();
   tail.dbg_noshared = dbg_noshared & 1;
+  tail.dbg_nomma = (dbg_noshared >> 2) & 1;
+  tail.dbg_nostore = (dbg_noshared >> 12) & 1;
   const bool l2keep = keep_mb > 0 && (num || epi) && L.nsplit == 1;
   if (l2keep) {
     const int64_t keep_rows = std::min<int64_t>(L.npad, (int64_t)keep_mb * 1000000 / (D * 4));
@@ -1879,6 +2006,8 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   e.reverse = l2keep ? 1 : 0;
   e.merged = merged ? 1 : 0;
   e.dbg_noshared = (dbg_noshared >> 1) & 1;
+  e.dbg_nomma = (dbg_noshared >> 3) & 1;
+  e.dbg = dbg_noshared >> 4;
   if (fuse_z) {
     e.zpart = zpart; e.nzpart = (int)cdiv(L.npad, fuse_z_rpb); e.zpart_stride = L.zpart_stride; e.z_out = z;
     e.z_only = epi ? 0 : 1;
@@ -1916,9 +2045,22 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
     else
       launch_ex(k_umma_accum_bal<2>, dim3(nb), dim3(UCfg<2>::kThreads), kUSmemBytes, st, pdl, tm_p, tm_hiB, tm_loB, num, D, (int)Q,
                 bf16_bank ? 0 : 1, (int)L.npad, bal, e);
-  } else if (G == 1) launch_accum<1>(al, st); else launch_accum<2>(al, st);
+  } else {
+    // plain fused correction of a dense, unsplit, unchunked pass: through the tile scratch + k_umma_untile
+    static const bool want_untile = [] { const char* e = getenv("SDN_UMMA_UNTILE"); return !(e && atoi(e) == 0); }();
+    if (want_untile && epi && L.bal && !sparse && !al.chunked && nsplit == 1 && e.x0 && z && (e.z || e.zpart) && !e.z_only)
+      al.e.tile_out = part;
+    if (G == 1) launch_accum<1>(al, st); else launch_accum<2>(al, st);
+  }
   g_prof.end(pid, st);
   SDN_LAUNCHED();
+  if (al.e.tile_out) {
+    pid = g_prof.begin("k_umma_untile", st);
+    launch_ex(k_umma_untile, dim3((unsigned)cdiv(Q * D / 4, 256)), dim3(256), 0, st, pdl, (const float*)part, e.x0, num, e.neg_out,
+              (const float*)z, e.eps, (int)Q, D, G, e.scale, e.mean_out, e.inv_qd);
+    g_prof.end(pid, st);
+    SDN_LAUNCHED();
+  }
   if (nsplit > 1) {
     pid = g_prof.begin("k_umma_splitsum", st);
     k_umma_splitsum<<<(unsigned)cdiv(Q * D, 1024), 256, 0, st>>>(part, nsplit, Q * D, Q * D, (int)Q, num,
