@@ -51,6 +51,21 @@ def test_host_only_entry_points(nv):
     assert L.sdn_launch_count() == 0
 
 
+def test_host_pipe_argument_checks(nv):
+    """sdn_host_pipe_*: every argument error is reported before any CUDA call (this box has no GPU)."""
+    import ctypes
+    L = nv.lib()
+    h = ctypes.c_void_p()
+    assert L.sdn_host_pipe_create(4, 100, 16384, 3, None) == -1            # no place for the handle
+    assert L.sdn_host_pipe_create(0, 100, 16384, 3, ctypes.byref(h)) == -2  # Q
+    assert L.sdn_host_pipe_create(4, 100, 16384, 0, ctypes.byref(h)) == -2  # slots: 1..8
+    assert L.sdn_host_pipe_create(4, 100, 16384, 9, ctypes.byref(h)) == -2
+    assert not h.value
+    assert L.sdn_host_pipe_submit(None, 0, None, None, None, None, None, None, 1.0, 1, 1.0, 1e-8, 0.3) == -1
+    assert L.sdn_host_pipe_wait(None, 0) == -1
+    L.sdn_host_pipe_destroy(None)                                           # a null handle is ignored
+
+
 def test_missing_library_is_loud(monkeypatch):
     from safe_denoiser_b200 import _native
     monkeypatch.setattr(_native, "_lib", None)
