@@ -1129,6 +1129,11 @@ k_umma_accum(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
             }
           }
         }
+      } else if (epi.tile_out) {                            // plain sums (partial-sums calls), through the tile scratch as well
+        const int dblock = (int)blockIdx.x + t * (int)gridDim.x;
+        float* const tp = epi.tile_out + (((int64_t)dblock * G + g) * kUQ + c * 32) * kUDBlock + lq * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tp[j * kUDBlock] = a[j];
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -1517,18 +1522,20 @@ k_umma_untile(const float* __restrict__ tiles, float* __restrict__ x0, float* __
     const int64_t db = d / kUDBlock;
     const int dl = (int)(d % kUDBlock);
     const float4 a = __ldcg(reinterpret_cast<const float4*>(tiles + ((db * G + g) * kUQ + ql) * kUDBlock + dl));
-    float4 x = __ldcg(reinterpret_cast<const float4*>(x0 + e));
-    const float ri = 1.f / (__ldcg(z + q) + eps);
-    const float4 n = make_float4(a.x * ri, a.y * ri, a.z * ri, a.w * ri);
-    x.x = fmaf(-scale, n.x, x.x);
-    x.y = fmaf(-scale, n.y, x.y);
-    x.z = fmaf(-scale, n.z, x.z);
-    x.w = fmaf(-scale, n.w, x.w);
-    *reinterpret_cast<float4*>(x0 + e) = x;
     if (num_out) *reinterpret_cast<float4*>(num_out + e) = a;
-    if (neg_out) *reinterpret_cast<float4*>(neg_out + e) = n;
-    m = fminf(fmaxf(n.x, -1e10f), 1e10f) + fminf(fmaxf(n.y, -1e10f), 1e10f) + fminf(fmaxf(n.z, -1e10f), 1e10f) +
-        fminf(fmaxf(n.w, -1e10f), 1e10f);
+    if (x0) {                           // null: a partial-sums call, only the sums go out (row-major)
+      float4 x = __ldcg(reinterpret_cast<const float4*>(x0 + e));
+      const float ri = 1.f / (__ldcg(z + q) + eps);
+      const float4 n = make_float4(a.x * ri, a.y * ri, a.z * ri, a.w * ri);
+      x.x = fmaf(-scale, n.x, x.x);
+      x.y = fmaf(-scale, n.y, x.y);
+      x.z = fmaf(-scale, n.z, x.z);
+      x.w = fmaf(-scale, n.w, x.w);
+      *reinterpret_cast<float4*>(x0 + e) = x;
+      if (neg_out) *reinterpret_cast<float4*>(neg_out + e) = n;
+      m = fminf(fmaxf(n.x, -1e10f), 1e10f) + fminf(fmaxf(n.y, -1e10f), 1e10f) + fminf(fmaxf(n.z, -1e10f), 1e10f) +
+          fminf(fmaxf(n.w, -1e10f), 1e10f);
+    }
   }
   if (mean_out) {                       // the reference's logging scalar: mean of the clamped projection
     m = warp_sum(m);
@@ -2048,16 +2055,22 @@ static int umma_pass(const void* planes, const float* sqnorm, int64_t N, int64_t
   } else {
     // plain fused correction of a dense, unsplit, unchunked pass: through the tile scratch + k_umma_untile
     static const bool want_untile = [] { const char* e = getenv("SDN_UMMA_UNTILE"); return !(e && atoi(e) == 0); }();
-    if (want_untile && epi && L.bal && !sparse && !al.chunked && nsplit == 1 && e.x0 && z && (e.z || e.zpart) && !e.z_only)
-      al.e.tile_out = part;
+    // partial-sums calls through the scratch too (SDN_UMMA_UNTILE_PARTIAL=1): measured neutral (N = 375: phase B 16.7 ->
+    // 14.7 us, one more launch, step 38.9 us both ways), so the N-sharded chain stays as it was validated on 8 GPUs
+    static const bool untile_partial = [] { const char* e = getenv("SDN_UMMA_UNTILE_PARTIAL"); return e && atoi(e) != 0; }();
+    const bool tileable = want_untile && L.bal && !sparse && !al.chunked && nsplit == 1;
+    if (tileable && epi && e.x0 && z && (e.z || e.zpart) && !e.z_only)
+      al.e.tile_out = part;                       // fused correction
+    else if (tileable && !epi && num && untile_partial)
+      al.e.tile_out = part;                       // partial sums (three-call sequence, N-sharded banks): k_umma_untile copies them out
     if (G == 1) launch_accum<1>(al, st); else launch_accum<2>(al, st);
   }
   g_prof.end(pid, st);
   SDN_LAUNCHED();
   if (al.e.tile_out) {
     pid = g_prof.begin("k_umma_untile", st);
-    launch_ex(k_umma_untile, dim3((unsigned)cdiv(Q * D / 4, 256)), dim3(256), 0, st, pdl, (const float*)part, e.x0, num, e.neg_out,
-              (const float*)z, e.eps, (int)Q, D, G, e.scale, e.mean_out, e.inv_qd);
+    launch_ex(k_umma_untile, dim3((unsigned)cdiv(Q * D / 4, 256)), dim3(256), 0, st, pdl, (const float*)part, epi ? e.x0 : nullptr, num,
+              epi ? e.neg_out : nullptr, (const float*)z, e.eps, (int)Q, D, G, e.scale, epi ? e.mean_out : nullptr, e.inv_qd);
     g_prof.end(pid, st);
     SDN_LAUNCHED();
   }
