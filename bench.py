@@ -694,9 +694,12 @@ def main():
                     "d2h_bytes_per_step": Q * D * 4 + Q * 4, "steps": e2e_pipe["steps"] if e2e_pipe and "steps" in e2e_pipe else e2e_steps,
                     "mode": (f"{e2e_pipe['in_flight']} independent host-buffer calls in flight (sdn_host_pipe_submit / _wait), wall clock "
                              "over the whole run, no L2 flush inside (the bank is larger than the L2)")
-                    if e2e_pipe and e2e_value == e2e_pipe.get("value") else "one synchronous host-buffer call at a time",
+                    if e2e_pipe and e2e_value == e2e_pipe.get("value")
+                    else ("one synchronous host-buffer call at a time" if world == 1
+                          else "one step at a time: pinned host -> graphed N-sharded step -> pinned host"),
                     "one_call_at_a_time": {"value": e2e_serial, "steps": e2e_steps,
-                                           "note": "sdn_conditioning_host, synchronous, L2 flushed between calls"},
+                                           "note": ("sdn_conditioning_host, synchronous" if world == 1 else "graphed N-sharded step fed from pinned host memory")
+                                           + ", L2 flushed between calls"},
                     "pipelined": e2e_pipe},
             "parity_check": parity,
             "roofline": {"bound": "hbm",
