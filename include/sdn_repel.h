@@ -208,8 +208,10 @@ int sdn_epilogue_flow(const float* num, const float* z, int64_t Q, int64_t D,
  * no channel normalisation (fast.py:120-132, threshold.py:171-193).
  *   Q <= 8 : the one-pass kernel computes ||x||^2 itself and the per-cluster reduction applies the correction
  *            (2 launches);
- *   Q > 8  : (needs `planes` and z_out) query planes + ||x||^2 in one kernel, correction fused into the epilogue
- *            of phase B (5 launches instead of 8).  One pass over the bank serves up to 128 query rows (two groups
+ *   Q > 8  : (needs `planes` and z_out) query planes + ||x||^2 in one kernel, phase A, weights, phase B (which also sums
+ *            z), and a row-contiguous kernel that applies the correction from phase B's tile scratch (5 launches
+ *            instead of 8; chunked / split / block-sparse passes correct in phase B's epilogue: 4).  One pass over
+ *            the bank serves up to 128 query rows (two groups
  *            of 64 sharing every bank tile; the small element-wise kernels run once per group), more rows take
  *            ceil(Q / 128) passes.
  * x0_inout [Q,D] is corrected in place; num_out / neg_out / k_out are optional extra outputs; mean_out is zeroed
